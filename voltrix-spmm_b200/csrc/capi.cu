@@ -1,0 +1,132 @@
+// capi.cu -- extern "C" surface of libvoltrix_b200.so (declared in include/voltrix_b200.h).
+// Thin forwarding only: every kernel lives in the header templates under csrc/voltrix/, which are
+// also what the JIT-generated `launch` stubs include.
+#include "voltrix_b200.h"
+
+#include "voltrix/bmat_kernels.cuh"
+#include "voltrix/schedule.cuh"
+#include "voltrix/spmm_kernels.cuh"
+
+using namespace voltrix;
+
+static_assert(sizeof(vx_work_item_t) == sizeof(WorkItem), "ABI mismatch");
+static_assert(sizeof(vx_fixup_item_t) == sizeof(FixupItem), "ABI mismatch");
+static_assert(sizeof(vx_schedule_counts_t) == sizeof(ScheduleCounts), "ABI mismatch");
+
+template <typename T>
+static int spmm_dispatch(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind,
+                         int32_t num_nodes, int32_t num_edges, int32_t embedding_dim, const void *input,
+                         float *output, int32_t model, int32_t stages, const SpmmPlan &plan, cudaStream_t stream) {
+  const T *in = static_cast<const T *>(input);
+  if (stages == 32)
+    return voltrix_spmm_forward_cuda<T, 32>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, in,
+                                            output, model, plan, stream);
+  if (stages == 8)
+    return voltrix_spmm_forward_cuda<T, 8>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, in,
+                                           output, model, plan, stream);
+  return voltrix_spmm_forward_cuda<T, 16>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, in,
+                                          output, model, plan, stream);
+}
+
+extern "C" {
+
+int vx_abi_version(void) { return 1; }
+
+size_t vx_preprocess_workspace_bytes(int64_t num_edges, int32_t num_nodes) {
+  return preprocess_workspace_bytes(num_edges, num_nodes);
+}
+
+int vx_preprocess(const int32_t *edge_list, const int32_t *node_pointer, int32_t num_nodes, int64_t num_edges,
+                  int32_t *block_partition, int32_t *edge_to_column, int32_t *edge_to_row, int32_t *pointer1,
+                  void *workspace, size_t workspace_bytes, void *stream) {
+  return preprocess(edge_list, node_pointer, num_nodes, num_edges, BLK_H, BLK_W, block_partition, edge_to_column,
+                    edge_to_row, pointer1, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int vx_hmat_gen(const int32_t *node_pointer, const int32_t *edge_list, const int32_t *block_partition,
+                const int32_t *edge_to_column, const int32_t *edge_to_row, const int32_t *pointer1,
+                int32_t num_row_windows, int32_t num_nodes, int64_t num_edges, float *hspa, int32_t *hind,
+                void *stream) {
+  return hmat_cuda(node_pointer, edge_list, block_partition, edge_to_column, edge_to_row, pointer1, num_row_windows,
+                   num_nodes, num_edges, hspa, hind, (cudaStream_t)stream);
+}
+
+int vx_hmat_packed_swizzle(int32_t num_row_windows, const int32_t *pointer1, const float *hspa,
+                           uint32_t *hspa_packed, void *stream) {
+  return hmat_packed_swizzle_cuda(num_row_windows, pointer1, hspa, hspa_packed, (cudaStream_t)stream);
+}
+
+int vx_csr_window_sort(const int32_t *indptr, const int32_t *indices, int32_t num_nodes, int64_t num_edges,
+                       int32_t num_cols, int32_t *block_partition, int32_t *pointer1, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+  PreprocessWorkspace ws;
+  int rc = carve_workspace(workspace, workspace_bytes, num_edges, num_nodes, ws);
+  if (rc != VX_OK) return rc;
+  return csr_window_sort(indptr, indices, num_nodes, num_edges, num_cols, ws, block_partition, pointer1, nullptr,
+                         (cudaStream_t)stream);
+}
+
+int vx_csr_tiles_scatter(int32_t num_nodes, int64_t num_edges, int32_t num_cols, const int32_t *pointer1,
+                         int64_t total_blocks, int32_t *hind, uint32_t *hspa_packed, int64_t *unique_nnz,
+                         void *workspace, size_t workspace_bytes, void *stream) {
+  PreprocessWorkspace ws;
+  int rc = carve_workspace(workspace, workspace_bytes, num_edges, num_nodes, ws);
+  if (rc != VX_OK) return rc;
+  return csr_tiles_scatter(num_nodes, num_edges, num_cols, ws, pointer1, total_blocks, hind, hspa_packed,
+                           unique_nnz, (cudaStream_t)stream);
+}
+
+int64_t vx_schedule_max_items(int32_t num_nodes, int64_t total_blocks, int32_t cap) {
+  return schedule_max_items(ceil_div<int32_t>(num_nodes, BLK_H), total_blocks, cap);
+}
+
+size_t vx_schedule_workspace_bytes(int32_t num_nodes, int64_t max_items) {
+  return schedule_workspace_bytes(ceil_div<int32_t>(num_nodes, BLK_H), max_items);
+}
+
+int vx_schedule_build(const int32_t *pointer1, const int32_t *indptr, int32_t num_nodes, int32_t cap,
+                      float sparse_ratio, int64_t max_items, vx_fixup_item_t *fixups, int32_t *sparse_rows,
+                      vx_schedule_counts_t *counts, void *workspace, size_t workspace_bytes, void *stream) {
+  return build_schedule(pointer1, indptr, num_nodes, cap, sparse_ratio, max_items,
+                        reinterpret_cast<FixupItem *>(fixups), sparse_rows,
+                        reinterpret_cast<ScheduleCounts *>(counts), workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int vx_schedule_sort(int32_t num_items, int32_t num_nodes, int64_t max_items, vx_work_item_t *items,
+                     void *workspace, size_t workspace_bytes, void *stream) {
+  return sort_schedule(num_items, ceil_div<int32_t>(num_nodes, BLK_H), max_items,
+                       reinterpret_cast<WorkItem *>(items), workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind, int32_t num_nodes,
+            int32_t num_edges, int32_t embedding_dim, const void *input, int32_t input_dtype, float *output,
+            int32_t model, int32_t stages, const vx_plan_t *plan, void *stream) {
+  SpmmPlan p;
+  if (plan) {
+    p.items = reinterpret_cast<const WorkItem *>(plan->items);
+    p.num_items = plan->num_items;
+    p.fixups = reinterpret_cast<const FixupItem *>(plan->fixups);
+    p.num_fixups = plan->num_fixups;
+    p.scratch = plan->scratch;
+    p.csr_indptr = plan->csr_indptr;
+    p.csr_indices = plan->csr_indices;
+    p.sparse_rows = plan->sparse_rows;
+    p.num_sparse_rows = plan->num_sparse_rows;
+    p.input_rows = plan->input_rows;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (input_dtype) {
+    case VX_DTYPE_F32:
+      return spmm_dispatch<float>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, input, output,
+                                  model, stages, p, s);
+    case VX_DTYPE_F16:
+      return spmm_dispatch<__half>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, input, output,
+                                   model, stages, p, s);
+    case VX_DTYPE_BF16:
+      return spmm_dispatch<__nv_bfloat16>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, input,
+                                          output, model, stages, p, s);
+  }
+  return VX_ERR_INVALID_ARG;
+}
+
+}  // extern "C"

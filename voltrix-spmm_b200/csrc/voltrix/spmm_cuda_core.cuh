@@ -1,0 +1,200 @@
+// spmm_cuda_core.cuh -- vectorised CUDA-core SpMM paths.
+//
+// Two kernels, both fp32-accumulating and exact for fp32 input (no TF32 rounding):
+//
+//  * vx_csr_rows_kernel   -- one warp per output row, straight from CSR.  Lane groups of
+//    LANES threads cover one B-row slice with 16-byte loads; 32/LANES groups walk the row's
+//    non-zeros in parallel, 4 deep, and are shuffle-reduced at the end.  This is the path for
+//    windows too sparse to fill an MMA tile (north_star subsystem 3): it gathers exactly
+//    nnz(row) B rows, whereas a 16x8 TC block always gathers 8.
+//
+//  * vx_tile_rows_kernel  -- one warp per output row, from the reference tile format
+//    (blk_offsets, hspa_packed, hind) only.  Used when a caller hands us nothing but the
+//    reference triple (kernel-level API) and the tcgen05 path does not apply (N % 64 != 0).
+//
+// The reference has no CUDA-core path; its only kernels are the mma.sync pipelines at
+// voltrix/include/voltrix/spmm_kernels.cuh:1458-2001.  Semantics follow SURVEY.md Appendix A:
+// C[row, :] = sum over distinct columns c of row of B[c, :], fp32 accumulation.
+#ifndef VOLTRIX_B200_SPMM_CUDA_CORE_CUH_
+#define VOLTRIX_B200_SPMM_CUDA_CORE_CUH_
+
+#include "voltrix/common.cuh"
+
+namespace voltrix {
+
+template <typename T> struct Vec16;  // 16 bytes of T, unpacked to fp32
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  __device__ static void add(float (&acc)[4], const uint4 &v) {
+    acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y);
+    acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
+  }
+};
+template <> struct Vec16<__half> {
+  static constexpr int N = 8;
+  __device__ static void add(float (&acc)[8], const uint4 &v) {
+    const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(h[i]);
+      acc[2 * i] += f.x; acc[2 * i + 1] += f.y;
+    }
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void add(float (&acc)[8], const uint4 &v) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
+      acc[2 * i] += __uint_as_float(w[i] << 16);
+      acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
+__device__ __forceinline__ uint4 vx_ldg16(const void *p) {
+  return __ldg(reinterpret_cast<const uint4 *>(p));
+}
+
+// rows: either all rows [0, num_rows) (row_list == nullptr) or the rows named by
+// row_list[0..num_rows).  grid.x * warps_per_block >= num_rows, grid.y = feature chunks.
+template <typename T, int LANES>
+__global__ void __launch_bounds__(256)
+vx_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                   const int32_t *__restrict__ row_list, int32_t num_rows, int32_t N,
+                   const T *__restrict__ B, float *__restrict__ C) {
+  constexpr int EPL = Vec16<T>::N;            // elements per lane per load
+  constexpr int GROUPS = 32 / LANES;          // non-zeros processed in parallel by one warp
+  constexpr int CHUNK = LANES * EPL;          // features covered by one pass
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LANES;               // position inside the row slice
+  const int grp = lane / LANES;
+  const int32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (item >= num_rows) return;
+  const int32_t row = row_list ? row_list[item] : item;
+  const int32_t f0 = blockIdx.y * CHUNK + sub * EPL;
+  const bool active = f0 < N;
+  const int32_t beg = indptr[row], end = indptr[row + 1];
+
+  float acc[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
+
+  const T *Bf = B + f0;
+  int32_t e = beg + grp;
+  // 4 independent gathers in flight per lane group
+  for (; e + 3 * GROUPS < end; e += 4 * GROUPS) {
+    int32_t c0 = __ldg(indices + e), c1 = __ldg(indices + e + GROUPS);
+    int32_t c2 = __ldg(indices + e + 2 * GROUPS), c3 = __ldg(indices + e + 3 * GROUPS);
+    if (active) {
+      uint4 v0 = vx_ldg16(Bf + int64_t(c0) * N), v1 = vx_ldg16(Bf + int64_t(c1) * N);
+      uint4 v2 = vx_ldg16(Bf + int64_t(c2) * N), v3 = vx_ldg16(Bf + int64_t(c3) * N);
+      Vec16<T>::add(acc, v0); Vec16<T>::add(acc, v1);
+      Vec16<T>::add(acc, v2); Vec16<T>::add(acc, v3);
+    }
+  }
+  for (; e < end; e += GROUPS) {
+    int32_t c0 = __ldg(indices + e);
+    if (active) Vec16<T>::add(acc, vx_ldg16(Bf + int64_t(c0) * N));
+  }
+  // fixed-order tree reduction over the lane groups (deterministic)
+#pragma unroll
+  for (int off = 16; off >= LANES; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+  }
+  if (grp == 0 && active) {
+    float4 *dst = reinterpret_cast<float4 *>(C + int64_t(row) * N + f0);
+#pragma unroll
+    for (int i = 0; i < EPL / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+  }
+}
+
+// One warp per row of the tile format.  Lane l scans TC block (b0 + l) of the row's window for
+// its 8-bit column mask, then the warp walks the set bits together: every step all 32 lanes load
+// one 512-byte slice of one B row.
+template <typename T>
+__global__ void __launch_bounds__(256)
+vx_tile_rows_kernel(const int32_t *__restrict__ blk_offsets, const uint32_t *__restrict__ packed,
+                    const int32_t *__restrict__ hind, int32_t num_nodes, int32_t N,
+                    const T *__restrict__ B, float *__restrict__ C) {
+  constexpr int EPL = Vec16<T>::N;
+  constexpr int CHUNK = 32 * EPL;
+  const int lane = threadIdx.x & 31;
+  const int32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= num_nodes) return;
+  const int32_t w = row >> 4, r = row & 15;
+  const int32_t f0 = blockIdx.y * CHUNK + lane * EPL;
+  const bool active = f0 < N;
+  const int64_t bb = blk_offsets[w], be = blk_offsets[w + 1];
+  const int word = r >> 3, shift = (r & 7) << 2;
+
+  float acc[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
+  const T *Bf = B + f0;
+
+  for (int64_t b0 = bb; b0 < be; b0 += 32) {
+    int64_t b = b0 + lane;
+    uint32_t mask = 0;
+    if (b < be) {
+      uint32_t lo = __ldg(packed + b * 4 + word), hi = __ldg(packed + b * 4 + word + 2);
+      mask = ((lo >> shift) & 0xfu) | (((hi >> shift) & 0xfu) << 4);
+    }
+    uint32_t ballot = __ballot_sync(0xffffffffu, mask != 0);
+    while (ballot) {
+      int src = __ffs(ballot) - 1;
+      ballot &= ballot - 1;
+      uint32_t m = __shfl_sync(0xffffffffu, mask, src);
+      const int32_t *cols = hind + (b0 + src) * BLK_W;
+      while (m) {
+        int c = __ffs(m) - 1;
+        m &= m - 1;
+        int32_t col = __ldg(cols + c);
+        if (active) Vec16<T>::add(acc, vx_ldg16(Bf + int64_t(col) * N));
+      }
+    }
+  }
+  if (active) {
+    float4 *dst = reinterpret_cast<float4 *>(C + int64_t(row) * N + f0);
+#pragma unroll
+    for (int i = 0; i < EPL / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+template <typename T>
+inline int launch_csr_rows(const int32_t *indptr, const int32_t *indices, const int32_t *row_list, int32_t num_rows,
+                           int32_t N, const T *B, float *C, cudaStream_t stream) {
+  constexpr int EPL = Vec16<T>::N;
+  if (num_rows <= 0) return VX_OK;
+  if (N <= 0 || N % EPL != 0) return VX_ERR_UNSUPPORTED;
+  int lanes_needed = N / EPL;  // 16-byte loads per row
+  dim3 block(256);
+  auto grid = [&](int lanes) { return dim3(ceil_div(num_rows, 8), ceil_div(N, lanes * EPL)); };
+  if (lanes_needed <= 4)       vx_csr_rows_kernel<T, 4><<<grid(4), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+  else if (lanes_needed <= 8)  vx_csr_rows_kernel<T, 8><<<grid(8), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+  else if (lanes_needed <= 16) vx_csr_rows_kernel<T, 16><<<grid(16), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+  else                         vx_csr_rows_kernel<T, 32><<<grid(32), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+  VX_LAUNCH_CHECK();
+  return VX_OK;
+}
+
+template <typename T>
+inline int launch_tile_rows(const int32_t *blk_offsets, const uint32_t *packed, const int32_t *hind,
+                            int32_t num_nodes, int32_t N, const T *B, float *C, cudaStream_t stream) {
+  constexpr int EPL = Vec16<T>::N;
+  if (num_nodes <= 0) return VX_OK;
+  if (N <= 0 || N % EPL != 0) return VX_ERR_UNSUPPORTED;
+  dim3 block(256), grid(ceil_div(num_nodes, 8), ceil_div(N, 32 * EPL));
+  vx_tile_rows_kernel<T><<<grid, block, 0, stream>>>(blk_offsets, packed, hind, num_nodes, N, B, C);
+  VX_LAUNCH_CHECK();
+  return VX_OK;
+}
+
+}  // namespace voltrix
+
+#endif  // VOLTRIX_B200_SPMM_CUDA_CORE_CUH_

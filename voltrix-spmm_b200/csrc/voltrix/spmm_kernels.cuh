@@ -1,0 +1,85 @@
+// spmm_kernels.cuh -- the SpMM entry point behind voltrix.spmm / spmm_kernel.
+//
+// Mirrors the reference launcher's name and leading arguments
+// (voltrix::voltrix_spmm_forward_cuda, voltrix/include/voltrix/spmm_kernels.cuh:2003-2113) so that
+// the JIT template reads the same, but dispatches B200-native paths.  `model` is the autotuned key
+// (the reference's three models are mma.sync tile shapes, :2014-2108); here:
+//
+//   model 0  tensor-core path: tcgen05 + TMA gather4 persistent kernel over the work list, plus the
+//            CUDA-core row kernel for the windows the schedule classified as sparse.
+//   model 1  CUDA-core CSR path for every row (needs the CSR arrays kept in the plan; exact fp32).
+//   model 2  CUDA-core path straight from the tile format (needs nothing but the reference triple).
+//
+// Unlike the reference, nothing here throws or calls exit(): errors come back as VX_* codes.
+#ifndef VOLTRIX_B200_SPMM_KERNELS_CUH_
+#define VOLTRIX_B200_SPMM_KERNELS_CUH_
+
+#include "voltrix/common.cuh"
+#include "voltrix/spmm_cuda_core.cuh"
+#include "voltrix/spmm_tcgen05.cuh"
+
+namespace voltrix {
+
+// Optional per-matrix state produced by csr_preprocess (all device pointers; any may be null).
+struct SpmmPlan {
+  const WorkItem *items = nullptr;       // LPT-sorted tensor-core work list
+  int32_t num_items = 0;
+  const FixupItem *fixups = nullptr;     // K-split windows
+  int32_t num_fixups = 0;
+  float *scratch = nullptr;              // [num_slots][16][N] fp32 partial tiles
+  const int32_t *csr_indptr = nullptr;   // coalesced CSR (for the CUDA-core row path)
+  const int32_t *csr_indices = nullptr;
+  const int32_t *sparse_rows = nullptr;  // rows of the windows routed to the CUDA-core path
+  int32_t num_sparse_rows = 0;
+  int64_t input_rows = 0;                // rows of the dense operand (0 = num_nodes, i.e. square A);
+                                         // differs for a row shard of A, whose columns span the full matrix
+};
+
+template <typename T> struct TcSupported { static constexpr bool value = false; };
+template <> struct TcSupported<__half> { static constexpr bool value = true; };
+template <> struct TcSupported<__nv_bfloat16> { static constexpr bool value = true; };
+
+template <typename T, int STAGES = 16>
+inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t *hspa_packed, const int32_t *hind,
+                                     int num_nodes, int num_edges, int embedding_dim, const T *input, float *output,
+                                     int model, const SpmmPlan &plan, cudaStream_t stream) {
+  (void)num_edges;
+  if (num_nodes < 0 || embedding_dim <= 0) return VX_ERR_INVALID_ARG;
+  if (num_nodes == 0) return VX_OK;
+  const int32_t W = ceil_div<int32_t>(num_nodes, BLK_H);
+  const int64_t b_rows = plan.input_rows > 0 ? plan.input_rows : num_nodes;
+  if (model == 0) {
+    if constexpr (TcSupported<T>::value) {
+      int rc;
+      if (plan.items != nullptr) {
+        if (plan.num_fixups > 0 && plan.scratch == nullptr) return VX_ERR_INVALID_ARG;
+        rc = launch_spmm_tc<T, STAGES>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
+                                       hspa_packed, hind, num_nodes, b_rows, embedding_dim, input,
+                                       output, plan.scratch, stream);
+        if (rc != VX_OK) return rc;
+        if (plan.num_sparse_rows > 0) {
+          if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows) return VX_ERR_INVALID_ARG;
+          rc = launch_csr_rows<T>(plan.csr_indptr, plan.csr_indices, plan.sparse_rows, plan.num_sparse_rows,
+                                  embedding_dim, input, output, stream);
+        }
+      } else {
+        rc = launch_spmm_tc<T, STAGES>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind, num_nodes, b_rows,
+                                       embedding_dim, input, output, nullptr, stream);
+      }
+      return rc;
+    } else {
+      return VX_ERR_UNSUPPORTED;
+    }
+  } else if (model == 1) {
+    if (!plan.csr_indptr || !plan.csr_indices) return VX_ERR_INVALID_ARG;
+    return launch_csr_rows<T>(plan.csr_indptr, plan.csr_indices, nullptr, num_nodes, embedding_dim, input, output,
+                              stream);
+  } else if (model == 2) {
+    return launch_tile_rows<T>(blks_offsets, hspa_packed, hind, num_nodes, embedding_dim, input, output, stream);
+  }
+  return VX_ERR_INVALID_ARG;
+}
+
+}  // namespace voltrix
+
+#endif  // VOLTRIX_B200_SPMM_KERNELS_CUH_

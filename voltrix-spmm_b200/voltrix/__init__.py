@@ -1,0 +1,6 @@
+"""voltrix -- B200-native drop-in for the Voltrix-SpMM hot path (reference: voltrix/__init__.py:1-3)."""
+from .project import *  # noqa: F401,F403
+from .jit_kernels import *  # noqa: F401,F403
+from .spmm import *  # noqa: F401,F403
+from .spmm import BLK_H, BLK_W, csr_preprocess, spmm, SpmmPlan  # noqa: F401  (`spmm` the function shadows the sub-package, as in the reference)
+from . import jit, jit_kernels, project, utils  # noqa: F401

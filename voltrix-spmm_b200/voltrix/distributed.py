@@ -1,0 +1,137 @@
+"""Row-sharded multi-GPU SpMM (new functionality: the reference is single-GPU).
+
+Output rows are independent and a 16-row window is the atomic unit, so A is cut into contiguous,
+window-aligned row ranges of (nearly) equal weight -- nnz by default, TC blocks if the caller has them --
+one per rank.  Each rank preprocesses only its shard.  The only exchange step of the path is making B
+available everywhere: one NCCL broadcast (B is needed in full by every shard, because any shard may
+reference any column).  C stays row-sharded; ``all_gather`` materialises it on every rank on request
+(shards are padded to the largest one, NCCL all_gather needs equal sizes).
+
+Window alignment makes shard windows coincide with the single-GPU windows, so the concatenated shard
+outputs are bit-identical to the 1-GPU result.
+
+One process per GPU, ``torch.distributed`` for the plumbing (backend nccl on GPUs; the host logic is
+covered with gloo on CPU in tests/test_distributed.py, where the local SpMM is injected).
+"""
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+BLK_H = 16
+
+
+def partition_rows(weights: torch.Tensor, world_size: int, align: int = BLK_H) -> List[Tuple[int, int]]:
+    """Contiguous, ``align``-aligned row ranges minimising the heaviest shard (bottleneck-optimal).
+
+    ``weights[r]`` is the cost of row r (its nnz, or its share of the window's TC blocks).  The smallest
+    per-shard budget L for which a greedy left-to-right packing of whole windows fits in ``world_size``
+    shards is found by bisection (each probe is ``world_size`` binary searches on the window prefix sums),
+    then that packing is returned.  A hub window heavier than the ideal share becomes a shard of its own;
+    trailing shards may be empty when there are fewer windows than ranks.  Deterministic: every rank
+    computes the same answer from the same input.
+    """
+    M = int(weights.numel())
+    W = (M + align - 1) // align
+    if W == 0:
+        return [(0, 0)] * world_size
+    w = weights.to(torch.int64).cpu()
+    pad = W * align - M
+    if pad:
+        w = torch.cat([w, torch.zeros(pad, dtype=w.dtype)])
+    ww = w.view(W, align).sum(1)
+    prefix = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(ww, 0)])   # prefix[i] = weight of windows [0, i)
+    total, heaviest = int(prefix[-1]), int(ww.max())
+
+    def pack(limit: int):
+        cuts, start = [0], 0
+        for _ in range(world_size):
+            if start >= W:
+                cuts.append(W)
+                continue
+            # furthest end with prefix[end] - prefix[start] <= limit
+            end = int(torch.searchsorted(prefix, prefix[start] + limit, right=True)) - 1
+            end = max(end, start + 1) if limit >= int(ww[start]) else start   # a window over budget: infeasible
+            if end == start:
+                return None
+            cuts.append(min(end, W))
+            start = cuts[-1]
+        return cuts if start >= W else None
+
+    lo, hi = max(heaviest, (total + world_size - 1) // world_size), max(total, 1)
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if pack(mid) is not None:
+            hi = mid
+        else:
+            lo = mid + 1
+    cuts = pack(lo)
+    return [(min(cuts[k] * align, M), min(cuts[k + 1] * align, M)) for k in range(world_size)]
+
+
+def shard_csr(indptr: torch.Tensor, indices: torch.Tensor, r0: int, r1: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    lo, hi = int(indptr[r0]), int(indptr[r1])
+    return (indptr[r0:r1 + 1] - lo).to(torch.int32).contiguous(), indices[lo:hi].contiguous()
+
+
+class ShardedSpMM:
+    """Per-rank state of a row-sharded SpMM.
+
+    ``local_preprocess(indptr, indices, num_rows, num_cols)`` and ``local_spmm(state, feat) -> C_local`` default
+    to the CUDA path (``voltrix.csr_preprocess`` / ``voltrix.spmm``) and raise without a GPU; tests inject CPU
+    stand-ins to exercise the partitioning / collective logic under gloo.
+    """
+
+    def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, num_nodes: int,
+                 weights: Optional[torch.Tensor] = None, group=None,
+                 local_preprocess: Optional[Callable] = None, local_spmm: Optional[Callable] = None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.num_nodes = num_nodes
+        if weights is None:
+            weights = (indptr[1:] - indptr[:-1])
+        self.ranges = partition_rows(weights, self.world)
+        self.r0, self.r1 = self.ranges[self.rank]
+        self.local_rows = self.r1 - self.r0
+        lp, li = shard_csr(indptr, indices, self.r0, self.r1)
+        self.local_nnz = int(li.numel())
+        if local_preprocess is None:
+            from .spmm import csr_preprocess
+            local_preprocess = lambda ip, ix, rows, cols: csr_preprocess(ip, ix, rows, num_cols=cols)  # noqa: E731
+        if local_spmm is None:
+            from .spmm import spmm as _spmm
+            local_spmm = lambda st, feat: _spmm(st[0], st[1], st[2], self.local_rows, self.local_nnz, feat)  # noqa: E731
+        self._spmm = local_spmm
+        self.state = local_preprocess(lp, li, self.local_rows, num_nodes) if self.local_rows > 0 else None
+
+    # -- the one exchange step of the path --------------------------------------------------------
+    def broadcast_features(self, feat: torch.Tensor, src: int = 0) -> torch.Tensor:
+        """Make the full dense operand resident on every rank (NCCL broadcast over NVLink/NVSwitch)."""
+        if self.world > 1:
+            dist.broadcast(feat, src=src, group=self.group)
+        return feat
+
+    def spmm(self, feat: torch.Tensor) -> torch.Tensor:
+        """C[r0:r1, :] for this rank; ``feat`` is the FULL dense operand, already resident."""
+        if self.local_rows == 0:
+            return torch.empty((0, feat.shape[1]), dtype=torch.float32, device=feat.device)
+        return self._spmm(self.state, feat)
+
+    def all_gather(self, c_local: torch.Tensor) -> torch.Tensor:
+        """Optional: full C on every rank.  Shards are padded to the largest row count."""
+        if self.world == 1:
+            return c_local
+        n = c_local.shape[1]
+        max_rows = max(b - a for a, b in self.ranges)
+        padded = torch.zeros((max_rows, n), dtype=c_local.dtype, device=c_local.device)
+        padded[: c_local.shape[0]] = c_local
+        out = torch.empty((self.world, max_rows, n), dtype=c_local.dtype, device=c_local.device)
+        dist.all_gather_into_tensor(out.view(-1, n), padded, group=self.group) if c_local.is_cuda else \
+            dist.all_gather(list(out.unbind(0)), padded, group=self.group)
+        return torch.cat([out[k, : b - a] for k, (a, b) in enumerate(self.ranges)], 0)
+
+    def imbalance(self, weights: Sequence[float]) -> float:
+        """max / mean of per-rank weights (1.0 = perfect)."""
+        w = list(weights)
+        return max(w) / (sum(w) / len(w)) if sum(w) else 1.0

@@ -1,0 +1,57 @@
+"""Ahead-of-time population of the JIT cache (every kernel variant the autotuner can pick).
+
+Called by ``__graft_entry__.build()`` on the GPU-less build box: nvcc cross-compiles sm_100a there, the
+cache directory is in-tree, so the GPU box starts with a warm cache and never waits on nvcc.
+"""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import torch
+
+from . import bmat_swizzle, hmat_gem, preprocess, spmm, tiles
+from .tuner import jit_tuner
+
+
+def _hmat_arg_defs():
+    return (("node_pointer", torch.int), ("edge_list", torch.int), ("block_partition", torch.int),
+            ("edge_to_column", torch.int), ("edge_to_row", torch.int), ("pointer1", torch.int),
+            ("num_row_windows", int), ("num_nodes", int), ("num_edges", int), ("hspa", torch.float),
+            ("hind", torch.int), ("stream", torch.cuda.Stream))
+
+
+def _swizzle_arg_defs():
+    return (("num_row_windows", int), ("pointer1", torch.int), ("hspa", torch.float),
+            ("hspa_packed", torch.uint32), ("stream", torch.cuda.Stream))
+
+
+def all_variants():
+    """(name, keys, space, includes, arg_defs, template) for every artefact."""
+    out = [
+        ("preprocess_kernel", {}, tuple(), preprocess.includes, preprocess.arg_defs, preprocess.template),
+        ("hmat_gen_kernel", {}, tuple(), hmat_gem.includes, _hmat_arg_defs(), hmat_gem.template),
+        ("hmat_packed_swizzle_kernel", {}, tuple(), bmat_swizzle.includes, _swizzle_arg_defs(), bmat_swizzle.template),
+        ("csr_tiles_kernel", {}, tuple(), tiles._tiles_includes, tiles._tiles_arg_defs, tiles._tiles_template),
+        ("schedule_kernel", {}, tuple(), tiles._sched_includes, tiles._sched_arg_defs, tiles._sched_template),
+    ]
+    for dtype, ctype in spmm._CTYPE.items():
+        space = spmm.SPACE_FP32 if dtype == torch.float32 else spmm.SPACE_HALF
+        out.append(("spmm_kernel", {"ctype": ctype}, space, spmm.includes, spmm.arg_defs_for(dtype), spmm.template))
+    return out
+
+
+def precompile_all(verbose: bool = False):
+    variants = all_variants()
+    jobs = []
+    for name, keys, space, includes, arg_defs, template in variants:
+        for code, tuned in jit_tuner.candidates(keys, space, includes, arg_defs, template):
+            jobs.append((name, arg_defs, code, tuned))
+    from .tuner import _build_one
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(lambda j: _build_one(*j), jobs))
+    failed = [(j[0], j[3], r[2]) for j, r in zip(jobs, results) if r[0] is None]
+    if failed:
+        raise RuntimeError("JIT prebuild failed:\n" + "\n".join(f"{n} {k}: {e}" for n, k, e in failed))
+    if verbose:
+        for j, r in zip(jobs, results):
+            print(f"  built {j[0]} {j[3]} -> {os.path.basename(r[0].path)}")
+    return [r[0] for r in results]

@@ -1,0 +1,129 @@
+"""``spmm_kernel``: the SpMM launch, JIT-specialised and autotuned.
+
+Reference: voltrix/jit_kernels/spmm.py:17-94.  Same positional / keyword arguments and the same
+autotune protocol (``jit_tuner.compile_and_tune`` over a ``model`` space, tuning key derived from
+``hspa_packed.hash_tag``), with these extensions:
+
+* ``input`` may be fp32 (exact fp32 CUDA-core paths), fp16 or bf16 (tcgen05 path, fp32 accumulate);
+* the tuning key also carries N and the dtype;
+* an optional ``plan`` (hung off ``hspa_packed`` by ``csr_preprocess``) supplies the nnz-balanced work
+  list and the CSR arrays; without it only the reference triple is used;
+* the generated ``launch`` writes ``__return_code``; candidates that cannot run a configuration
+  report a non-zero code and are skipped by the tuner instead of killing the process.
+"""
+import warnings
+
+import torch
+
+from ..jit.compiler import hash_to_hex
+from ._common import check, current_stream
+from .tuner import jit_tuner
+
+includes = ('"voltrix/spmm_kernels.cuh"',)
+template = """
+voltrix::SpmmPlan plan;
+plan.items = reinterpret_cast<const voltrix::WorkItem*>(items);
+plan.num_items = num_items;
+plan.fixups = reinterpret_cast<const voltrix::FixupItem*>(fixups);
+plan.num_fixups = num_fixups;
+plan.scratch = scratch;
+plan.csr_indptr = csr_indptr;
+plan.csr_indices = csr_indices;
+plan.sparse_rows = sparse_rows;
+plan.num_sparse_rows = num_sparse_rows;
+plan.input_rows = input_rows;
+__return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}>(
+    blk_offsets, hspa_packed, hind,
+    num_nodes, num_edges, embedding_dim, input, output, {model}, plan, stream);
+"""
+
+_CTYPE = {torch.float32: "float", torch.float16: "__half", torch.bfloat16: "__nv_bfloat16"}
+
+# autotune space per input dtype: (model, stages)
+SPACE_HALF = ({"model": 0, "stages": 16}, {"model": 0, "stages": 32}, {"model": 1, "stages": 16},
+              {"model": 2, "stages": 16})
+SPACE_FP32 = ({"model": 1, "stages": 16}, {"model": 2, "stages": 16})
+
+
+def arg_defs_for(dtype):
+    return (
+        ("blk_offsets", torch.int32),
+        ("hspa_packed", torch.uint32),
+        ("hind", torch.int32),
+        ("num_nodes", int),
+        ("num_edges", int),
+        ("embedding_dim", int),
+        ("input", dtype),
+        ("output", torch.float32),
+        ("items", torch.int32),
+        ("num_items", int),
+        ("fixups", torch.int32),
+        ("num_fixups", int),
+        ("scratch", torch.float32),
+        ("csr_indptr", torch.int32),
+        ("csr_indices", torch.int32),
+        ("sparse_rows", torch.int32),
+        ("num_sparse_rows", int),
+        ("input_rows", int),
+        ("stream", torch.cuda.Stream),
+    )
+
+
+def feature_hash(feature: torch.Tensor) -> str:
+    """Tuning key of a matrix (reference: jit_kernels/spmm.py:17-36): ``hash_tag`` if set, else the address."""
+    if hasattr(feature, "hash_tag") and isinstance(feature.hash_tag, str):
+        return hash_to_hex(feature.hash_tag)
+    plan = getattr(feature, "_vx_plan", None)
+    if plan is not None:
+        return hash_to_hex(plan.signature())   # shape statistics of the matrix: stable across processes
+    warnings.warn(
+        "The feature tensor(i.e. `hspa_packed`)'s hash_tag attr is not set. "
+        "Voltrix will use the memory address as the key value for profiling, "
+        "which may lead to performance degradation of different cases."
+    )
+    return hash_to_hex(str(feature.data_ptr()))
+
+
+def spmm_kernel(
+    blk_offsets: torch.Tensor,  # pointer1
+    hspa_packed: torch.Tensor,
+    hind: torch.Tensor,
+    num_nodes: int,
+    num_edges: int,
+    embedding_dim: int,
+    input: torch.Tensor,
+    output: torch.Tensor,
+    plan=None,
+    model=None,
+    stages=None,
+):
+    assert blk_offsets.is_cuda and blk_offsets.dtype == torch.int32
+    assert hspa_packed.is_cuda and hspa_packed.dtype == torch.uint32
+    assert hind.is_cuda and hind.dtype == torch.int32
+    assert input.is_cuda and input.dtype in _CTYPE and input.is_contiguous()
+    assert output.is_cuda and output.dtype == torch.float and output.is_contiguous()
+    assert input.shape[-1] == embedding_dim and output.shape[-1] == embedding_dim
+
+    if plan is None:
+        plan = getattr(hspa_packed, "_vx_plan", None)
+    p = plan.launch_args(embedding_dim) if plan is not None else (None, 0, None, 0, None, None, None, None, 0)
+    args = (blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, input, output, *p,
+            int(input.shape[0]), current_stream())
+
+    if model is not None:   # explicit variant (tests, benchmarks): a space of one, no timing runs
+        space = ({"model": int(model), "stages": int(stages or 16)},)
+        keys = {"ctype": _CTYPE[input.dtype], "fixed": f"{model}/{stages or 16}"}
+    else:
+        space = SPACE_FP32 if input.dtype == torch.float32 else SPACE_HALF
+        keys = {"ctype": _CTYPE[input.dtype], "feature_hash": feature_hash(hspa_packed), "N": embedding_dim}
+    runtime = jit_tuner.compile_and_tune(
+        name="spmm_kernel",
+        keys=keys,
+        space=space,
+        includes=includes,
+        arg_defs=arg_defs_for(input.dtype),
+        template=template,
+        args=args,
+        kernel_tag="spmm",
+    )
+    check(runtime(*args), "spmm_kernel")

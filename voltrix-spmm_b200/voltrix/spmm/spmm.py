@@ -1,0 +1,192 @@
+"""Public op API: ``csr_preprocess`` and ``spmm``.
+
+Drop-in for the reference's voltrix/spmm/spmm.py:16-114 -- same names, argument order and return
+values: ``csr_preprocess(indptr, indices, num_nodes) -> (blk_offsets, hspa_packed, hind)`` (three CUDA
+tensors, bit-identical to the reference's) and ``spmm(blk_offsets, hspa_packed, hind, num_nodes,
+num_edges, feat) -> fp32 [num_nodes, N]``.
+
+What differs underneath:
+* preprocessing runs on the GPU end to end (the reference's column compaction is a single host
+  thread) and never materialises the fp32 ``hspa`` tiles;
+* ``csr_preprocess`` also builds the nnz-balanced work list and keeps the CSR arrays on the device; this
+  state rides along as ``hspa_packed._vx_plan`` (callers treat the triple as opaque except for setting
+  ``hspa_packed.hash_tag``, reference tests/test_spmm.py:55);
+* inputs may already live on the GPU; ``feat`` may be fp32, fp16 or bf16;
+* every output row is written, including the ``num_nodes % 16`` tail rows the reference leaves
+  uninitialised.
+There is no CPU fallback: without a CUDA device these functions raise.
+"""
+import math
+from typing import Optional
+
+import torch
+
+from ..jit_kernels import (
+    csr_tiles_scatter_kernel,
+    csr_window_sort_kernel,
+    preprocess_workspace_bytes,
+    schedule_build_kernel,
+    schedule_sizes,
+    schedule_sort_kernel,
+    spmm_kernel,
+)
+from ..jit_kernels._common import alloc_workspace, require_cuda
+
+BLK_H = 16
+BLK_W = 8
+
+# A window goes to the CUDA-core row path when gathering its nnz rows one by one moves fewer than
+# SPARSE_RATIO x the rows the tensor-core path would gather for it (16 per K-step).
+DEFAULT_SPARSE_RATIO = 0.5
+
+
+class SpmmPlan:
+    """Per-matrix device state produced by ``csr_preprocess`` and consumed by ``spmm``."""
+
+    def __init__(self):
+        self.num_nodes = 0
+        self.num_edges = 0
+        self.total_blocks = 0
+        self.unique_nnz = 0
+        self.cap = 0
+        self.sparse_ratio = 0.0
+        self.items: Optional[torch.Tensor] = None        # int32 [num_items, 4]  (window, blk_begin, blk_count, slot)
+        self.fixups: Optional[torch.Tensor] = None       # int32 [num_fixups, 4] (window, slot_begin, slot_count, 0)
+        self.sparse_rows: Optional[torch.Tensor] = None  # int32 [num_sparse_rows]
+        self.num_items = 0
+        self.num_slots = 0
+        self.num_fixups = 0
+        self.num_sparse_rows = 0
+        self.csr_indptr: Optional[torch.Tensor] = None
+        self.csr_indices: Optional[torch.Tensor] = None
+        self.block_partition: Optional[torch.Tensor] = None
+        self._scratch = {}
+
+    @property
+    def has_duplicates(self) -> bool:
+        return self.unique_nnz != self.num_edges
+
+    def signature(self) -> str:
+        return f"M{self.num_nodes}_E{self.num_edges}_B{self.total_blocks}_I{self.num_items}_S{self.num_sparse_rows}"
+
+    def scratch(self, embedding_dim: int) -> Optional[torch.Tensor]:
+        if self.num_slots == 0:
+            return None
+        buf = self._scratch.get(embedding_dim)
+        if buf is None:
+            buf = torch.empty(self.num_slots * BLK_H * embedding_dim, dtype=torch.float32, device=self.items.device)
+            self._scratch[embedding_dim] = buf
+        return buf
+
+    def launch_args(self, embedding_dim: int):
+        """The plan part of the spmm ``launch`` argument list (see jit_kernels/spmm.py::arg_defs_for)."""
+        return (self.items, self.num_items, self.fixups if self.num_fixups else None, self.num_fixups,
+                self.scratch(embedding_dim), self.csr_indptr, self.csr_indices,
+                self.sparse_rows if self.num_sparse_rows else None, self.num_sparse_rows)
+
+
+def _sm_count(device) -> int:
+    return torch.cuda.get_device_properties(device).multi_processor_count
+
+
+def csr_preprocess(
+    indptr: torch.Tensor,
+    indices: torch.Tensor,
+    num_nodes: int,
+    sparse_ratio: float = DEFAULT_SPARSE_RATIO,
+    keep_csr: bool = True,
+    num_cols: Optional[int] = None,
+):
+    """``num_cols`` (extension): number of columns of A when it is not square -- a row shard of a larger
+    matrix has ``num_nodes`` rows but columns spanning the whole graph."""
+    assert indptr.dtype == torch.int32 and indices.dtype == torch.int32
+    assert indptr.numel() == num_nodes + 1
+    require_cuda()
+    dev = indptr.device if indptr.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    indptr = indptr.contiguous().to(dev, non_blocking=True)
+    indices = indices.contiguous().to(dev, non_blocking=True)
+
+    num_edges = indices.numel()
+    num_row_windows = math.ceil(num_nodes / BLK_H)
+    num_cols = int(num_cols) if num_cols is not None else num_nodes
+
+    # phase 1: (window, column) sort, distinct-column ranks, TC blocks per window
+    workspace = alloc_workspace(preprocess_workspace_bytes(num_edges, num_nodes), dev)
+    block_partition = torch.empty(num_row_windows, dtype=torch.int32, device=dev)
+    pointer1 = torch.empty(num_row_windows + 1, dtype=torch.int32, device=dev)
+    csr_window_sort_kernel(indptr, indices, num_nodes, num_cols, block_partition, pointer1, workspace)
+
+    total_blocks = int(pointer1[-1].item())   # the one host sync the reference also has (spmm/spmm.py:44)
+
+    # phase 2: bitmaps + column lists, straight from the sorted edges
+    hind = torch.empty(total_blocks * BLK_W, dtype=torch.int32, device=dev)
+    hspa_packed = torch.empty(total_blocks * BLK_H * BLK_W // 32, dtype=torch.uint32, device=dev)
+    unique_nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+    csr_tiles_scatter_kernel(num_nodes, num_edges, num_cols, pointer1, total_blocks, hind, hspa_packed, unique_nnz,
+                             workspace)
+
+    plan = SpmmPlan()
+    plan.num_nodes, plan.num_edges, plan.total_blocks = num_nodes, num_edges, total_blocks
+    plan.block_partition = block_partition
+    plan.unique_nnz = int(unique_nnz.item())
+    del workspace
+
+    # The CUDA-core CSR path sums every stored entry, the tile format counts a duplicated (row, col)
+    # once (reference bmat_kernels.cuh:102): only keep the CSR arrays when the input is coalesced.
+    use_csr = keep_csr and not plan.has_duplicates
+    if use_csr:
+        plan.csr_indptr, plan.csr_indices = indptr, indices
+    plan.sparse_ratio = float(sparse_ratio) if use_csr else 0.0
+
+    # phase 3: nnz-balanced schedule.  A window is split along K only when it alone would exceed ~1/8 of
+    # an SM's share of the TC blocks.
+    cap = max(64, (total_blocks // (_sm_count(dev) * 8)) & ~1)
+    plan.cap = cap
+    max_items, sched_ws_bytes = schedule_sizes(num_nodes, total_blocks, cap)
+    sched_ws = alloc_workspace(sched_ws_bytes, dev)
+    fixups = torch.empty((max(num_row_windows, 1), 4), dtype=torch.int32, device=dev)
+    sparse_rows = torch.empty(max(num_nodes, 1), dtype=torch.int32, device=dev)
+    counts = torch.zeros(4, dtype=torch.int32, device=dev)
+    schedule_build_kernel(pointer1, plan.csr_indptr if plan.sparse_ratio > 0 else None, num_nodes, total_blocks, cap,
+                          plan.sparse_ratio, fixups, sparse_rows, counts, sched_ws)
+    plan.num_items, plan.num_slots, plan.num_fixups, plan.num_sparse_rows = (int(v) for v in counts.tolist())
+    items = torch.empty((max(plan.num_items, 1), 4), dtype=torch.int32, device=dev)
+    schedule_sort_kernel(plan.num_items, num_nodes, total_blocks, cap, items, sched_ws)
+    plan.items = items
+    plan.fixups = fixups[: max(plan.num_fixups, 1)].clone()
+    plan.sparse_rows = sparse_rows[: max(plan.num_sparse_rows, 1)].clone()
+    torch.cuda.current_stream().synchronize()
+    del sched_ws
+
+    hspa_packed._vx_plan = plan
+    return (
+        pointer1,  # blk_offsets
+        hspa_packed,
+        hind,
+    )
+
+
+def spmm(
+    blk_offsets: torch.Tensor,  # pointer1
+    hspa_packed: torch.Tensor,
+    hind: torch.Tensor,
+    num_nodes: int,
+    num_edges: int,
+    feat: torch.Tensor,
+    out: Optional[torch.Tensor] = None,
+):
+    num_feats = feat.shape[1]
+    output = out if out is not None else torch.empty((num_nodes, num_feats), dtype=torch.float32, device=feat.device)
+
+    spmm_kernel(
+        blk_offsets,
+        hspa_packed,
+        hind,
+        num_nodes=num_nodes,
+        num_edges=num_edges,
+        embedding_dim=num_feats,
+        input=feat,
+        output=output,
+    )
+
+    return output
