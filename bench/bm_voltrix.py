@@ -1,0 +1,43 @@
+"""Benchmark entry point (reference: bench/bm_voltrix.py:1-37) -- same inputs from the CWD, same two output
+lines (`difference rate: x.xxx%`, `[Voltrix] time: x.xxxx ms`, the latter parsed by bench_all.py).
+Extension: `--dtype fp16|bf16|fp32` (default fp32, the reference's only mode)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "voltrix-spmm_b200")))
+import voltrix  # noqa: E402
+from voltrix.utils import calc_diff, GPU_bench  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--dtype", default="fp32", choices=["fp32", "fp16", "bf16"])
+args, _ = ap.parse_known_args()
+DT = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
+
+
+def read_from_file(filename, dtype):
+    return np.fromfile(filename, dtype=dtype)
+
+
+indices = torch.tensor(np.loadtxt("indices.csv", delimiter=",", dtype=np.int32), dtype=torch.int32)
+indptr = torch.tensor(np.loadtxt("indptr.csv", delimiter=",", dtype=np.int32), dtype=torch.int32)
+N = indptr.numel() - 1
+weight = torch.tensor(read_from_file("feat.csv", np.float32)).cuda().view(N, -1).to(DT)
+
+blk_ofs, hspa_packed, hind = voltrix.csr_preprocess(indptr, indices, N)
+
+
+def spmm():
+    return voltrix.spmm(blk_ofs, hspa_packed, hind, num_nodes=N, num_edges=indices.numel(), feat=weight)
+
+
+o = spmm().detach().cpu()
+o_base = torch.tensor(read_from_file("output_base.csv", np.float32).reshape(*list(o.shape)))
+print(f"difference rate: {calc_diff(o, o_base) * 100:.3f}%")
+
+# kernel time with an L2 flush per iteration: all kernels of the call whose name contains "vx_" are summed
+time = GPU_bench(spmm, iters=10, warmup=10, kernel_name="vx_")
+print(f"[Voltrix] time: {time:.4f} ms")

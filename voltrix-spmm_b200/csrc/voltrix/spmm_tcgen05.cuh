@@ -317,11 +317,9 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
   if (rc != VX_OK) return rc;
   auto kern = vx_spmm_tc_kernel<T, STAGES>;
   constexpr size_t smem = tc_smem_bytes<STAGES>();
-  static bool attr_set = false;
-  if (!attr_set) {
-    VX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr_set = true;
-  }
+  // Set on every launch (~1 us): a function-local `static bool` would be a GNU_UNIQUE symbol shared by every
+  // JIT artefact / library that instantiates this template, while each of them owns a distinct kernel copy.
+  VX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int32_t n_feat_tiles = ceil_div(N, TcGeom::kFeatTile);
   const int64_t total_units = int64_t(num_items) * n_feat_tiles;
   const int grid = int(total_units < device_sm_count() ? total_units : device_sm_count());

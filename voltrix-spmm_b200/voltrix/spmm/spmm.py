@@ -135,7 +135,9 @@ def csr_preprocess(
     # once (reference bmat_kernels.cuh:102): only keep the CSR arrays when the input is coalesced.
     use_csr = keep_csr and not plan.has_duplicates
     if use_csr:
-        plan.csr_indptr, plan.csr_indices = indptr, indices
+        # an edgeless matrix still needs a non-null indices pointer for the launch ABI
+        plan.csr_indptr = indptr
+        plan.csr_indices = indices if num_edges > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
     plan.sparse_ratio = float(sparse_ratio) if use_csr else 0.0
 
     # phase 3: nnz-balanced schedule.  A window is split along K only when it alone would exceed ~1/8 of
