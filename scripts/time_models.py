@@ -39,18 +39,17 @@ print(f"{desc}: M={M} nnz={nnz} N={N} TCB={plan.total_blocks} items={plan.num_it
 feat = torch.rand(M, N, device=dev).to(dt)
 out = torch.empty(M, N, device=dev)
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
-variants = [(0, 8), (0, 16), (0, 32), (1, 16), (2, 16)] if dt != torch.float32 else [(1, 16), (2, 16)]
+variants = [(0, 16, 4), (0, 32, 8), (0, 36, 12), (1, 32, 8), (2, 32, 8)] if dt != torch.float32 else [(1, 32, 8), (2, 32, 8)]
 if args.only:
-    m, s = args.only.split("/")
-    variants = [(int(m), int(s))]
+    variants = [tuple(int(x) for x in v.split("/")) for v in args.only.split(",")]
 ref = None
-for model, stages in variants:
+for model, stages, npw in variants:
     def run():
         voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=nnz, embedding_dim=N, input=feat, output=out,
-                            model=model, stages=stages)
+                            model=model, stages=stages, npw=npw)
     if args.once:
         run(); torch.cuda.synchronize(); flush.zero_(); run(); torch.cuda.synchronize()
-        print(f"ran model {model} stages {stages} once (after one warm-up)")
+        print(f"ran model {model} stages {stages} npw {npw} once (after one warm-up)")
         continue
     run(); torch.cuda.synchronize()
     if ref is None:
@@ -66,5 +65,5 @@ for model, stages in variants:
         ts.append(s.elapsed_time(e))
     ms = float(np.median(ts))
     gather = plan.total_blocks * 8 * N * feat.element_size() if model != 1 else nnz * N * feat.element_size()
-    print(f"model {model} stages {stages:2d}: {ms:8.3f} ms  {2.0 * nnz * N / ms / 1e6:9.1f} GFLOP/s  "
+    print(f"model {model} stages {stages:2d} npw {npw:2d}: {ms:8.3f} ms  {2.0 * nnz * N / ms / 1e6:9.1f} GFLOP/s  "
           f"gather {gather / ms / 1e6:8.1f} GB/s  (min {min(ts):.3f} max {max(ts):.3f})")

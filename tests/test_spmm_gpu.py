@@ -21,7 +21,7 @@ def _scaled_err(got, want):
 
 def _run_all_models(voltrix, blk, packed, hind, M, E, feat):
     out = {}
-    models = [(1, 16), (2, 16)] if feat.dtype == torch.float32 else [(0, 16), (0, 32), (1, 16), (2, 16)]
+    models = [(1, 32), (2, 32)] if feat.dtype == torch.float32 else [(0, 16), (0, 32), (0, 36), (1, 32), (2, 32)]
     for model, stages in models:
         o = torch.full((M, feat.shape[1]), float("nan"), device="cuda")
         try:

@@ -18,14 +18,17 @@ static int spmm_dispatch(const int32_t *blk_offsets, const uint32_t *hspa_packed
                          int32_t num_nodes, int32_t num_edges, int32_t embedding_dim, const void *input,
                          float *output, int32_t model, int32_t stages, const SpmmPlan &plan, cudaStream_t stream) {
   const T *in = static_cast<const T *>(input);
-  if (stages == 32)
-    return voltrix_spmm_forward_cuda<T, 32>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, in,
-                                            output, model, plan, stream);
-  if (stages == 8)
-    return voltrix_spmm_forward_cuda<T, 8>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, in,
-                                           output, model, plan, stream);
-  return voltrix_spmm_forward_cuda<T, 16>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, in,
-                                          output, model, plan, stream);
+  // `stages` = K-steps (16 gathered rows each) in flight; the number of producer warps follows from it
+#define VX_TC_VARIANT(KS, NPW)                                                                                   \
+  return voltrix_spmm_forward_cuda<T, KS, NPW>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, in, \
+                                               output, model, plan, stream)
+  switch (stages) {
+    case 8: VX_TC_VARIANT(8, 4);
+    case 16: VX_TC_VARIANT(16, 4);
+    case 36: VX_TC_VARIANT(36, 12);
+    default: VX_TC_VARIANT(32, 8);
+  }
+#undef VX_TC_VARIANT
 }
 
 extern "C" {

@@ -273,7 +273,9 @@ inline int grid_for(int64_t n, int threads) { return int(ceil_div<int64_t>(n > 0
 inline int csr_window_sort(const int32_t *indptr, const int32_t *indices, int32_t num_nodes, int64_t nnz,
                            int32_t num_cols, const PreprocessWorkspace &ws, int32_t *block_partition,
                            int32_t *pointer1, int32_t *edge_to_row, cudaStream_t stream) {
-  if (num_nodes < 0 || nnz < 0 || nnz >= (int64_t(1) << 31)) return VX_ERR_INVALID_ARG;
+  if (num_nodes < 0 || nnz < 0) return VX_ERR_INVALID_ARG;
+  // int32 offsets like the reference's: TCB <= nnz + W must fit pointer1 (shard larger matrices by rows)
+  if (nnz + ceil_div<int64_t>(num_nodes, BLK_H) >= (int64_t(1) << 31)) return VX_ERR_OVERFLOW;
   int32_t W = ceil_div<int32_t>(num_nodes, BLK_H);
   KeyBits kb = make_key_bits(num_nodes, num_cols);
   VX_CUDA_TRY(cudaMemsetAsync(pointer1, 0, sizeof(int32_t), stream));

@@ -39,7 +39,7 @@ template <typename T> struct TcSupported { static constexpr bool value = false; 
 template <> struct TcSupported<__half> { static constexpr bool value = true; };
 template <> struct TcSupported<__nv_bfloat16> { static constexpr bool value = true; };
 
-template <typename T, int STAGES = 16>
+template <typename T, int STAGES = 32, int NPW = 8>
 inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t *hspa_packed, const int32_t *hind,
                                      int num_nodes, int num_edges, int embedding_dim, const T *input, float *output,
                                      int model, const SpmmPlan &plan, cudaStream_t stream) {
@@ -53,7 +53,7 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
       int rc;
       if (plan.items != nullptr) {
         if (plan.num_fixups > 0 && plan.scratch == nullptr) return VX_ERR_INVALID_ARG;
-        rc = launch_spmm_tc<T, STAGES>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
+        rc = launch_spmm_tc<T, STAGES, NPW>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
                                        hspa_packed, hind, num_nodes, b_rows, embedding_dim, input,
                                        output, plan.scratch, stream);
         if (rc != VX_OK) return rc;
@@ -63,7 +63,7 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
                                   embedding_dim, input, output, stream);
         }
       } else {
-        rc = launch_spmm_tc<T, STAGES>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind, num_nodes, b_rows,
+        rc = launch_spmm_tc<T, STAGES, NPW>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind, num_nodes, b_rows,
                                        embedding_dim, input, output, nullptr, stream);
       }
       return rc;

@@ -11,14 +11,20 @@
 //     width fills the MMA M dimension and the 16-row window is the MMA N dimension;
 //   * Bg^T is the "A" operand, MN-major, SWIZZLE_128B: exactly the image TMA tile::gather4 leaves in
 //     shared memory (4 B rows x 128 B per instruction; two of them fill one 8-row swizzle atom);
-//   * A^T is the "B" operand, K-major, no swizzle: 512 B expanded from two 16-byte bitmaps by one warp;
+//   * A^T is the "B" operand, K-major, no swizzle: 512 B expanded from two 16-byte bitmaps;
 //   * D^T lives in TMEM (128 lanes x 16 fp32 columns, double buffered across work items) and is read
 //     back with tcgen05.ld 32x32b: a thread holds the 16 window rows of one feature, so every store
 //     instruction of a warp writes 32 consecutive floats of one C row;
-//   * warp roles: 0 = TMA gather producer (4 lanes per K-step, 8 K-steps in flight per pass),
-//     1 = MMA issuer (lane 0), 2 = bitmap expander, 3 = TMEM allocator, 4-7 = epilogue;
-//   * a ring of STAGES (B tile + A tile) slots guarded by full/empty mbarriers; tcgen05.commit frees a
-//     slot when the MMA that read it retires;
+//   * a K-step is 16 gathered rows (two TC blocks); a pipeline stage is 4 K-steps (16 KB of B rows + 2 KB
+//     of A^T), so the MMA warp pays one mbarrier wait and one tcgen05.commit per 64 gathered rows;
+//   * warp roles (10 warps): 0-3 producers -- warp w owns K-step w of every stage: it expands the two
+//     bitmaps into the A^T tile with all 32 lanes, then ONE elected lane issues the 8 gather4 copies
+//     (elect.sync keeps the TMA operands in uniform registers: no per-lane serialisation loop);
+//     4-7 epilogue (TMEM lane quarter = warp % 4); 8 = MMA issuer + TMEM owner; 9 = metadata loader,
+//     which streams each item's hind / bitmap arrays into a shared-memory ring with 1-D bulk copies so
+//     the producers never wait on a global load;
+//   * full/empty mbarriers per stage (tcgen05.commit frees a stage when the MMAs that read it retire),
+//     full/empty per metadata chunk, full/empty per TMEM accumulator;
 //   * persistent CTAs stride over the LPT-sorted work list (schedule.cuh), every role derives the same
 //     item sequence independently, so no intra-CTA work broadcast is needed.
 #ifndef VOLTRIX_B200_SPMM_TCGEN05_CUH_
@@ -39,37 +45,59 @@ template <> struct TcFmt<__nv_bfloat16> {
   static constexpr CUtensorMapDataType kTmapType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 };
 
+template <int NPW>
 struct TcGeom {
   static constexpr int kFeatTile = 128;                 // MMA M: features per work unit
   static constexpr int kAtomCols = 64;                  // 128-byte swizzle span in 16-bit elements
-  static constexpr int kStageB = kFeatTile * 16 * 2;    // 16 gathered rows x 128 features x 2 B = 4096
-  static constexpr int kStageA = 16 * 16 * 2;           // densified 16 x 16 tile = 512
-  static constexpr int kThreads = 256;
+  static constexpr int kKsB = kFeatTile * 16 * 2;       // one K-step: 16 gathered rows x 128 features x 2 B = 4096
+  static constexpr int kKsA = 16 * 16 * 2;              // one K-step: densified 16 x 16 tile = 512
+  static constexpr int kKsPerStage = NPW;               // = number of producer warps (one K-step each per stage)
+  static constexpr int kStageB = kKsPerStage * kKsB;
+  static constexpr int kStageA = kKsPerStage * kKsA;
+  static constexpr int kStagesPerChunk = 4;             // metadata chunk = 4 stages
+  static constexpr int kChunkBlks = 2 * kKsPerStage * kStagesPerChunk;   // TC blocks per metadata chunk
+  static constexpr int kMetaSlots = 4;
+  static constexpr int kMetaH = kChunkBlks * 32;        // hind bytes per chunk
+  static constexpr int kMetaP = kChunkBlks * 16;        // bitmap bytes per chunk
+  static constexpr int kEpilogueWarp0 = (NPW + 3) / 4 * 4;   // epilogue warp e reads TMEM lanes 32*(warp % 4)...
+  static constexpr int kMmaWarp = kEpilogueWarp0 + 4, kLoaderWarp = kEpilogueWarp0 + 5;
+  static constexpr int kThreads = (kEpilogueWarp0 + 6) * 32;
   static constexpr uint32_t kTmemCols = 32;             // two 16-column accumulators
 };
 
-template <int STAGES>
+// KSTEPS = K-steps in flight (the autotuned "stages" knob): ring depth = KSTEPS / NPW stages.
+template <int KSTEPS, int NPW>
 constexpr size_t tc_smem_bytes() {
-  return size_t(STAGES) * (TcGeom::kStageB + TcGeom::kStageA) + (2 * STAGES + 4) * 8 + 16 + 1024 /*align slack*/;
+  using G = TcGeom<NPW>;
+  constexpr int S = KSTEPS / G::kKsPerStage;
+  return size_t(S) * (G::kStageB + G::kStageA) + size_t(G::kMetaSlots) * (G::kMetaH + G::kMetaP) +
+         (2 * S + 2 * G::kMetaSlots + 4) * 8 + 16 + 1024 /*align slack*/;
 }
 
-template <typename T, int STAGES>
-__global__ void __launch_bounds__(TcGeom::kThreads, 1)
+template <typename T, int KSTEPS, int NPW>
+__global__ void __launch_bounds__(TcGeom<NPW>::kThreads, 1)
 vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__restrict__ items, int32_t num_items,
                   int32_t n_feat_tiles, const int32_t *__restrict__ blk_offsets, const uint4 *__restrict__ packed,
                   const int4 *__restrict__ hind4, int32_t num_nodes, int32_t N, float *__restrict__ C,
                   float *__restrict__ scratch) {
-  static_assert(STAGES >= 8 && (STAGES & (STAGES - 1)) == 0, "STAGES must be a power of two >= 8");
+  using G = TcGeom<NPW>;
+  static_assert(KSTEPS >= 2 * NPW && KSTEPS % NPW == 0, "KSTEPS must be a multiple of NPW, at least 2 stages");
+  constexpr uint32_t S = KSTEPS / G::kKsPerStage;
+  constexpr uint32_t MR = G::kMetaSlots;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sB = sbase;                                   // [STAGES][4096]  1024-aligned atoms
-  const uint32_t sA = sB + STAGES * TcGeom::kStageB;           // [STAGES][512]
-  const uint32_t sBar = sA + STAGES * TcGeom::kStageA;         // full[STAGES], empty[STAGES], tfull[2], tempty[2]
-  const uint32_t sTmem = sBar + (2 * STAGES + 4) * 8;
+  const uint32_t sB = sbase;                               // [S][4 K-steps][4096]  1024-aligned atoms
+  const uint32_t sA = sB + S * G::kStageB;                 // [S][4 K-steps][512]
+  const uint32_t sMetaH = sA + S * G::kStageA;             // [MR][64 blocks][8 int32]
+  const uint32_t sMetaP = sMetaH + MR * G::kMetaH;         // [MR][64 blocks][4 uint32]
+  const uint32_t sBar = sMetaP + MR * G::kMetaP;           // full[S] empty[S] mfull[MR] mempty[MR] tfull[2] tempty[2]
+  const uint32_t sTmem = sBar + (2 * S + 2 * MR + 4) * 8;
   auto full_bar = [&](uint32_t s) { return sBar + s * 8; };
-  auto empty_bar = [&](uint32_t s) { return sBar + (STAGES + s) * 8; };
-  auto tfull_bar = [&](uint32_t a) { return sBar + (2 * STAGES + a) * 8; };
-  auto tempty_bar = [&](uint32_t a) { return sBar + (2 * STAGES + 2 + a) * 8; };
+  auto empty_bar = [&](uint32_t s) { return sBar + (S + s) * 8; };
+  auto mfull_bar = [&](uint32_t m) { return sBar + (2 * S + m) * 8; };
+  auto mempty_bar = [&](uint32_t m) { return sBar + (2 * S + MR + m) * 8; };
+  auto tfull_bar = [&](uint32_t a) { return sBar + (2 * S + 2 * MR + a) * 8; };
+  auto tempty_bar = [&](uint32_t a) { return sBar + (2 * S + 2 * MR + 2 + a) * 8; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t total_units = num_items * n_feat_tiles;
@@ -84,137 +112,178 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
     return it;
   };
 
-  if (warp == 1 && lane == 0) {
-    for (uint32_t s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(full_bar(s), 4 + 1);   // 4 producer lanes (arrive.expect_tx) + expander
-      ptx::mbar_init(empty_bar(s), 1);      // tcgen05.commit
+  if (warp == G::kMmaWarp) {
+    if (lane == 0) {
+      for (uint32_t s = 0; s < S; ++s) {
+        ptx::mbar_init(full_bar(s), G::kKsPerStage);   // one arrive(.expect_tx) per producer warp
+        ptx::mbar_init(empty_bar(s), 1);               // tcgen05.commit
+      }
+      for (uint32_t m = 0; m < MR; ++m) {
+        ptx::mbar_init(mfull_bar(m), 1);               // loader's arrive.expect_tx
+        ptx::mbar_init(mempty_bar(m), G::kKsPerStage); // one arrive per producer warp
+      }
+      for (uint32_t a = 0; a < 2; ++a) {
+        ptx::mbar_init(tfull_bar(a), 1);               // tcgen05.commit after the item's last MMA
+        ptx::mbar_init(tempty_bar(a), 4);              // one arrive per epilogue warp
+      }
+      ptx::fence_mbar_init();
     }
-    for (uint32_t a = 0; a < 2; ++a) {
-      ptx::mbar_init(tfull_bar(a), 1);      // tcgen05.commit after the item's last MMA
-      ptx::mbar_init(tempty_bar(a), 4);     // one arrive per epilogue warp
-    }
-    ptx::fence_mbar_init();
+    __syncwarp();
+    ptx::tmem_alloc<G::kTmemCols>(sTmem);
   }
   if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&tmap);
-  if (warp == 3) ptx::tmem_alloc<TcGeom::kTmemCols>(sTmem);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA gather producer
-    const int q = lane & 3;      // which 4 of the 16 gathered rows of the K-step
-    const int sub = lane >> 2;   // which of the 8 K-steps of this pass
-    uint32_t g = 0;
-    for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const WorkItem it = load_item(u / n_feat_tiles);
-      const int32_t c_base = (u % n_feat_tiles) * TcGeom::kFeatTile;
-      const int32_t nj = min(2, (N - c_base + TcGeom::kAtomCols - 1) / TcGeom::kAtomCols);
-      const int32_t nks = (it.blk_count + 1) >> 1;
-      for (int32_t ks0 = 0; ks0 < nks; ks0 += 8) {
-        const int32_t ks = ks0 + sub;
-        if (ks < nks) {
-          const uint32_t gg = g + ks, stage = gg % STAGES, par = ((gg / STAGES) & 1u) ^ 1u;
-          const int32_t blk = 2 * ks + (q >> 1);
-          int4 rows = make_int4(0, 0, 0, 0);   // K-step tail past an odd block count: row 0, bitmap bits are 0
-          if (blk < it.blk_count) rows = __ldg(hind4 + (int64_t(it.blk_begin + blk) * 2 + (q & 1)));
-          ptx::mbar_wait(empty_bar(stage), par);
-          // atom (k-group kg = q>>1, feature half j) sits at (kg*2 + j) * 1024; 4 rows = half an atom
-          const uint32_t dst = sB + stage * TcGeom::kStageB + (q >> 1) * 2048 + (q & 1) * 512;
-          ptx::mbar_arrive_expect_tx(full_bar(stage), nj * 512);
-          for (int32_t j = 0; j < nj; ++j)
-            ptx::tma_gather4(dst + j * 1024, &tmap, full_bar(stage), c_base + j * TcGeom::kAtomCols, rows.x, rows.y,
-                             rows.z, rows.w);
+  if (warp == G::kLoaderWarp) {
+    // ------------------------------------------------------------------ metadata loader (one lane)
+    if (ptx::elect_one()) {
+      uint32_t gc = 0;
+      for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const WorkItem it = load_item(u / n_feat_tiles);
+        for (int32_t b0 = 0; b0 < it.blk_count; b0 += G::kChunkBlks, ++gc) {
+          const uint32_t m = gc % MR;
+          const uint32_t nb = uint32_t(min(G::kChunkBlks, it.blk_count - b0));
+          ptx::mbar_wait(mempty_bar(m), ((gc / MR) & 1u) ^ 1u);
+          ptx::mbar_arrive_expect_tx(mfull_bar(m), nb * 48u);
+          ptx::bulk_g2s(sMetaH + m * G::kMetaH, hind4 + int64_t(it.blk_begin + b0) * 2, nb * 32u, mfull_bar(m));
+          ptx::bulk_g2s(sMetaP + m * G::kMetaP, packed + int64_t(it.blk_begin + b0), nb * 16u, mfull_bar(m));
         }
       }
-      g += nks;
     }
-  } else if (warp == 1) {
+  } else if (warp < G::kKsPerStage) {
+    // ------------------------------------------------------------------ producers: bitmap expansion + TMA gather
+    const int n = lane & 15;     // window row
+    const int kc = lane >> 4;    // which TC block of the K-step (= which 8-column chunk of K)
+    const uint32_t a_off = uint32_t(warp) * G::kKsA + (n >> 3) * 256 + kc * 128 + (n & 7) * 16;
+    const uint32_t word_off = uint32_t(n >> 3) * 4, shift = uint32_t(n & 7) << 2;
+    constexpr uint32_t one = TcFmt<T>::kOne;
+    uint32_t gs = 0, gc = 0;
+    for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const WorkItem it = load_item(u / n_feat_tiles);
+      const int32_t c_base = (u % n_feat_tiles) * G::kFeatTile;
+      const int32_t nj = min(2, (N - c_base + G::kAtomCols - 1) / G::kAtomCols);
+      const int32_t nks = (it.blk_count + 1) >> 1;
+      const int32_t nst = (nks + G::kKsPerStage - 1) / G::kKsPerStage;
+      for (int32_t st = 0; st < nst; ++st, ++gs) {
+        const uint32_t s = gs % S, par = (gs / S) & 1u;
+        const int32_t cst = st % G::kStagesPerChunk;         // stage within its metadata chunk
+        const uint32_t m = (gc + uint32_t(st / G::kStagesPerChunk)) % MR;
+        if (cst == 0) ptx::mbar_wait(mfull_bar(m), ((gc + uint32_t(st / G::kStagesPerChunk)) / MR) & 1u);
+        const int32_t ks = st * G::kKsPerStage + warp;
+        ptx::mbar_wait(empty_bar(s), par ^ 1u);
+        if (ks < nks) {
+          const int32_t lb = (cst * G::kKsPerStage + warp) * 2;           // first block of the K-step, chunk-local
+          const bool has_b1 = 2 * ks + 1 < it.blk_count;                  // odd block count: second half is empty
+          // A^T fragment of this lane: 8 K values (one TC block's 8 columns) of window row n
+          uint32_t lo = 0, hi = 0;
+          if (kc == 0 || has_b1) {
+            const uint32_t pa = sMetaP + m * G::kMetaP + uint32_t(lb + kc) * 16 + word_off;
+            lo = (ptx::lds32(pa) >> shift) & 0xfu;        // columns 0..3 of row n
+            hi = (ptx::lds32(pa + 8) >> shift) & 0xfu;    // columns 4..7
+          }
+          // two halves per word: bit i -> 16-bit 1.0 (no carries: the products occupy disjoint bit ranges)
+          const uint32_t v0 = ((lo & 1u) | ((lo & 2u) << 15)) * one, v1 = (((lo >> 2) & 1u) | ((lo & 8u) << 13)) * one;
+          const uint32_t v2 = ((hi & 1u) | ((hi & 2u) << 15)) * one, v3 = (((hi >> 2) & 1u) | ((hi & 8u) << 13)) * one;
+          ptx::sts128(sA + s * G::kStageA + a_off, v0, v1, v2, v3);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (ptx::elect_one()) {
+            const uint32_t ha = sMetaH + m * G::kMetaH + uint32_t(lb) * 32;
+            const int4 r0 = ptx::lds128(ha), r1 = ptx::lds128(ha + 16);
+            int4 r2 = make_int4(0, 0, 0, 0), r3 = make_int4(0, 0, 0, 0);   // tail: row 0, bitmap bits are 0
+            if (has_b1) { r2 = ptx::lds128(ha + 32); r3 = ptx::lds128(ha + 48); }
+            const uint32_t bar = full_bar(s);
+            ptx::mbar_arrive_expect_tx(bar, uint32_t(nj) * 2048u);
+            // atom (k-group kg, feature half j) sits at (kg*2 + j) * 1024; 4 rows = half an atom (512 B)
+            const uint32_t dst = sB + s * G::kStageB + uint32_t(warp) * G::kKsB;
+            // issued row-group-major so the 4 row coordinates of a group stay in place in the uniform registers
+            // and only destination / column change between the two feature halves
+            if (nj == 2) {
+              const int32_t c1 = c_base + G::kAtomCols;
+              ptx::tma_gather4(dst, &tmap, bar, c_base, r0.x, r0.y, r0.z, r0.w);
+              ptx::tma_gather4(dst + 1024, &tmap, bar, c1, r0.x, r0.y, r0.z, r0.w);
+              ptx::tma_gather4(dst + 512, &tmap, bar, c_base, r1.x, r1.y, r1.z, r1.w);
+              ptx::tma_gather4(dst + 1536, &tmap, bar, c1, r1.x, r1.y, r1.z, r1.w);
+              ptx::tma_gather4(dst + 2048, &tmap, bar, c_base, r2.x, r2.y, r2.z, r2.w);
+              ptx::tma_gather4(dst + 3072, &tmap, bar, c1, r2.x, r2.y, r2.z, r2.w);
+              ptx::tma_gather4(dst + 2560, &tmap, bar, c_base, r3.x, r3.y, r3.z, r3.w);
+              ptx::tma_gather4(dst + 3584, &tmap, bar, c1, r3.x, r3.y, r3.z, r3.w);
+            } else {
+              ptx::tma_gather4(dst, &tmap, bar, c_base, r0.x, r0.y, r0.z, r0.w);
+              ptx::tma_gather4(dst + 512, &tmap, bar, c_base, r1.x, r1.y, r1.z, r1.w);
+              ptx::tma_gather4(dst + 2048, &tmap, bar, c_base, r2.x, r2.y, r2.z, r2.w);
+              ptx::tma_gather4(dst + 2560, &tmap, bar, c_base, r3.x, r3.y, r3.z, r3.w);
+            }
+          }
+        } else if (lane == 0) {
+          ptx::mbar_arrive(full_bar(s));   // K-step past the item's end: nothing to load, keep the count
+        }
+        if (cst == G::kStagesPerChunk - 1 || st == nst - 1) {   // done with this metadata chunk
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(mempty_bar(m));
+        }
+      }
+      gc += uint32_t((it.blk_count + G::kChunkBlks - 1) / G::kChunkBlks);
+    }
+  } else if (warp == G::kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = ptx::make_idesc(TcFmt<T>::kFmt, /*A MN-major*/ true, /*B K-major*/ false, 128, 16);
-    uint32_t g = 0, unit = 0;
-    for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x, ++unit) {
+    uint32_t gs = 0, unit = 0;
+    for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
       const WorkItem it = load_item(u / n_feat_tiles);
       const int32_t nks = (it.blk_count + 1) >> 1;
+      if (nks == 0) continue;
+      const int32_t nst = (nks + G::kKsPerStage - 1) / G::kKsPerStage;
       const uint32_t acc = unit & 1u;
       ptx::mbar_wait(tempty_bar(acc), ((unit >> 1) & 1u) ^ 1u);
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * 16;
-      for (int32_t ks = 0; ks < nks; ++ks) {
-        const uint32_t gg = g + ks, stage = gg % STAGES;
-        ptx::mbar_wait(full_bar(stage), (gg / STAGES) & 1u);
+      for (int32_t st = 0; st < nst; ++st, ++gs) {
+        const uint32_t s = gs % S;
+        ptx::mbar_wait(full_bar(s), (gs / S) & 1u);
         ptx::tc_fence_after_sync();
-        if (lane == 0) {
-          // A = gathered rows: MN-major SW128, LBO = feature-atom stride (1024), SBO = k-group stride (2048)
-          const uint64_t a_desc = ptx::smem_desc(sB + stage * TcGeom::kStageB, 1024, 2048, ptx::kLayoutSw128);
-          // B = densified tile: K-major, no swizzle, LBO = k-chunk stride (128), SBO = 8-row group stride (256)
-          const uint64_t b_desc = ptx::smem_desc(sA + stage * TcGeom::kStageA, 128, 256, ptx::kLayoutNone);
-          ptx::umma_f16(d_tmem, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
-          ptx::umma_commit(empty_bar(stage));
-          if (ks == nks - 1) ptx::umma_commit(tfull_bar(acc));
+        if (ptx::elect_one()) {
+          const int32_t kn = min(G::kKsPerStage, nks - st * G::kKsPerStage);
+          for (int32_t k = 0; k < kn; ++k) {
+            // A = gathered rows: MN-major SW128, LBO = feature-atom stride (1024), SBO = k-group stride (2048)
+            const uint64_t a_desc = ptx::smem_desc(sB + s * G::kStageB + k * G::kKsB, 1024, 2048, ptx::kLayoutSw128);
+            // B = densified tile: K-major, no swizzle, LBO = k-chunk stride (128), SBO = 8-row group stride (256)
+            const uint64_t b_desc = ptx::smem_desc(sA + s * G::kStageA + k * G::kKsA, 128, 256, ptx::kLayoutNone);
+            ptx::umma_f16(d_tmem, a_desc, b_desc, idesc, (st | k) > 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(s));
+          if (st == nst - 1) ptx::umma_commit(tfull_bar(acc));
         }
         __syncwarp();
       }
-      g += nks;
+      ++unit;
     }
-  } else if (warp == 2) {
-    // ------------------------------------------------------------------ bitmap -> dense A^T tile
-    const int n = lane & 15;     // window row
-    const int kc = lane >> 4;    // which TC block of the K-step (= which 8-column chunk of K)
-    const uint32_t a_off = (n >> 3) * 256 + kc * 128 + (n & 7) * 16;
-    const int word = n >> 3, shift = (n & 7) << 2;
-    uint32_t g = 0;
+  } else if (warp >= G::kEpilogueWarp0 && warp < G::kEpilogueWarp0 + 4) {
+    // ------------------------------------------------------------------ epilogue: TMEM -> C
+    const int ew = warp - G::kEpilogueWarp0;   // == warp % 4: the TMEM lane quarter this warp may read
+    uint32_t unit = 0;
     for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
       const WorkItem it = load_item(u / n_feat_tiles);
-      const int32_t nks = (it.blk_count + 1) >> 1;
-      // one coalesced load covers 32 blocks = 16 K-steps; words are redistributed by shuffle
-      for (int32_t ks0 = 0; ks0 < nks; ks0 += 16) {
-        const int32_t myblk = 2 * ks0 + lane;
-        uint4 bits = make_uint4(0, 0, 0, 0);
-        if (myblk < it.blk_count) bits = __ldg(packed + it.blk_begin + myblk);
-        const int32_t kend = min(16, nks - ks0);
-        for (int32_t i = 0; i < kend; ++i) {
-          const int src = 2 * i + kc;
-          const uint32_t w0 = __shfl_sync(0xffffffffu, bits.x, src), w1 = __shfl_sync(0xffffffffu, bits.y, src);
-          const uint32_t w2 = __shfl_sync(0xffffffffu, bits.z, src), w3 = __shfl_sync(0xffffffffu, bits.w, src);
-          const uint32_t lo = ((word ? w1 : w0) >> shift) & 0xfu;   // columns 0..3 of row n
-          const uint32_t hi = ((word ? w3 : w2) >> shift) & 0xfu;   // columns 4..7
-          constexpr uint32_t one = TcFmt<T>::kOne;
-          uint4 v;
-          v.x = ((lo & 1u) ? one : 0u) | ((lo & 2u) ? (one << 16) : 0u);
-          v.y = ((lo & 4u) ? one : 0u) | ((lo & 8u) ? (one << 16) : 0u);
-          v.z = ((hi & 1u) ? one : 0u) | ((hi & 2u) ? (one << 16) : 0u);
-          v.w = ((hi & 4u) ? one : 0u) | ((hi & 8u) ? (one << 16) : 0u);
-          const uint32_t gg = g + ks0 + i, stage = gg % STAGES;
-          ptx::mbar_wait(empty_bar(stage), ((gg / STAGES) & 1u) ^ 1u);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + stage * TcGeom::kStageA + a_off),
-                       "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                       : "memory");
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(full_bar(stage));
-        }
-      }
-      g += nks;
-    }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue: TMEM -> C
-    const int ew = warp - 4;   // == warp % 4: the TMEM lane quarter this warp may read
-    uint32_t unit = 0;
-    for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x, ++unit) {
-      const WorkItem it = load_item(u / n_feat_tiles);
-      const int32_t f = (u % n_feat_tiles) * TcGeom::kFeatTile + ew * 32 + lane;
-      const uint32_t acc = unit & 1u;
-      ptx::mbar_wait(tfull_bar(acc), (unit >> 1) & 1u);
-      ptx::tc_fence_after_sync();
+      const int32_t f = (u % n_feat_tiles) * G::kFeatTile + ew * 32 + lane;
       uint32_t v[16];
-      ptx::tmem_ld_32x32b_x16(tmem_base + (uint32_t(ew * 32) << 16) + acc * 16, v);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+      if (it.blk_count > 0) {
+        const uint32_t acc = unit & 1u;
+        ptx::mbar_wait(tfull_bar(acc), (unit >> 1) & 1u);
+        ptx::tc_fence_after_sync();
+        ptx::tmem_ld_32x32b_x16(tmem_base + (uint32_t(ew * 32) << 16) + acc * 16, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+        ++unit;
+      } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = 0u;
+      }
       if (f < N) {
         float *dst;
         int32_t nrows = BLK_H;
@@ -233,7 +302,7 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 3) ptx::tmem_dealloc<TcGeom::kTmemCols>(tmem_base);
+  if (warp == G::kMmaWarp) ptx::tmem_dealloc<G::kTmemCols>(tmem_base);
 }
 
 // Sums the partial tiles of K-split windows in slot order (fixed order => deterministic).
@@ -303,7 +372,7 @@ inline int device_sm_count() {
 
 // Launch the tensor-core kernel over a prepared work list.  B must be 16-byte aligned with N % 8 == 0
 // (TMA global-stride rule); hind / hspa_packed must be 16-byte aligned.
-template <typename T, int STAGES>
+template <typename T, int STAGES, int NPW>
 inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupItem *fixups, int32_t num_fixups,
                           const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind,
                           int32_t num_nodes, int64_t b_rows,
@@ -315,15 +384,17 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
   CUtensorMap tmap;
   int rc = make_gather_tensor_map(&tmap, B, TcFmt<T>::kTmapType, 2, b_rows, N);
   if (rc != VX_OK) return rc;
-  auto kern = vx_spmm_tc_kernel<T, STAGES>;
-  constexpr size_t smem = tc_smem_bytes<STAGES>();
+  using G = TcGeom<NPW>;
+  auto kern = vx_spmm_tc_kernel<T, STAGES, NPW>;
+  constexpr size_t smem = tc_smem_bytes<STAGES, NPW>();
+  static_assert(smem <= 227 * 1024, "stage ring does not fit in shared memory");
   // Set on every launch (~1 us): a function-local `static bool` would be a GNU_UNIQUE symbol shared by every
   // JIT artefact / library that instantiates this template, while each of them owns a distinct kernel copy.
   VX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  const int32_t n_feat_tiles = ceil_div(N, TcGeom::kFeatTile);
+  const int32_t n_feat_tiles = ceil_div(N, G::kFeatTile);
   const int64_t total_units = int64_t(num_items) * n_feat_tiles;
   const int grid = int(total_units < device_sm_count() ? total_units : device_sm_count());
-  kern<<<grid, TcGeom::kThreads, smem, stream>>>(tmap, items, num_items, n_feat_tiles, blk_offsets,
+  kern<<<grid, G::kThreads, smem, stream>>>(tmap, items, num_items, n_feat_tiles, blk_offsets,
                                                  reinterpret_cast<const uint4 *>(hspa_packed),
                                                  reinterpret_cast<const int4 *>(hind), num_nodes, N, C, scratch);
   VX_LAUNCH_CHECK();

@@ -34,7 +34,7 @@ def all_variants():
         ("schedule_kernel", {}, tuple(), tiles._sched_includes, tiles._sched_arg_defs, tiles._sched_template),
     ]
     for dtype, ctype in spmm._CTYPE.items():
-        space = spmm.SPACE_FP32 if dtype == torch.float32 else spmm.SPACE_HALF
+        space = spmm.SPACE_FP32 if dtype == torch.float32 else spmm.SPACE_HALF + spmm.EXTRA_HALF
         out.append(("spmm_kernel", {"ctype": ctype}, space, spmm.includes, spmm.arg_defs_for(dtype), spmm.template))
     return out
 

@@ -32,7 +32,7 @@ plan.csr_indices = csr_indices;
 plan.sparse_rows = sparse_rows;
 plan.num_sparse_rows = num_sparse_rows;
 plan.input_rows = input_rows;
-__return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}>(
+__return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}, {npw}>(
     blk_offsets, hspa_packed, hind,
     num_nodes, num_edges, embedding_dim, input, output, {model}, plan, stream);
 """
@@ -40,9 +40,11 @@ __return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}>(
 _CTYPE = {torch.float32: "float", torch.float16: "__half", torch.bfloat16: "__nv_bfloat16"}
 
 # autotune space per input dtype: (model, stages)
-SPACE_HALF = ({"model": 0, "stages": 16}, {"model": 0, "stages": 32}, {"model": 1, "stages": 16},
-              {"model": 2, "stages": 16})
-SPACE_FP32 = ({"model": 1, "stages": 16}, {"model": 2, "stages": 16})
+SPACE_HALF = ({"model": 0, "stages": 32, "npw": 8}, {"model": 0, "stages": 36, "npw": 12},
+              {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
+# variants reachable only through the explicit model=/stages= arguments (tests, scripts): prebuilt as well
+EXTRA_HALF = ({"model": 0, "stages": 16, "npw": 4},)
+SPACE_FP32 = ({"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
 
 
 def arg_defs_for(dtype):
@@ -96,6 +98,7 @@ def spmm_kernel(
     plan=None,
     model=None,
     stages=None,
+    npw=None,
 ):
     assert blk_offsets.is_cuda and blk_offsets.dtype == torch.int32
     assert hspa_packed.is_cuda and hspa_packed.dtype == torch.uint32
@@ -111,8 +114,9 @@ def spmm_kernel(
             int(input.shape[0]), current_stream())
 
     if model is not None:   # explicit variant (tests, benchmarks): a space of one, no timing runs
-        space = ({"model": int(model), "stages": int(stages or 16)},)
-        keys = {"ctype": _CTYPE[input.dtype], "fixed": f"{model}/{stages or 16}"}
+        stages, npw = int(stages or 32), int(npw or {8: 4, 16: 4, 36: 12}.get(int(stages or 32), 8))
+        space = ({"model": int(model), "stages": stages, "npw": npw},)
+        keys = {"ctype": _CTYPE[input.dtype], "fixed": f"{model}/{stages}/{npw}"}
     else:
         space = SPACE_FP32 if input.dtype == torch.float32 else SPACE_HALF
         keys = {"ctype": _CTYPE[input.dtype], "feature_hash": feature_hash(hspa_packed), "N": embedding_dim}
