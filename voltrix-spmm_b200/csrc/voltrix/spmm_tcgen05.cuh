@@ -51,7 +51,10 @@ struct TcGeom {
   static constexpr int kAtomCols = 64;                  // 128-byte swizzle span in 16-bit elements
   static constexpr int kKsB = kFeatTile * 16 * 2;       // one K-step: 16 gathered rows x 128 features x 2 B = 4096
   static constexpr int kKsA = 16 * 16 * 2;              // one K-step: densified 16 x 16 tile = 512
-  static constexpr int kKsPerStage = NPW;               // = number of producer warps (one K-step each per stage)
+  // K-steps per stage.  Up to 12 producer warps: one stage = one K-step per warp.  More warps: stages of 8
+  // K-steps owned round-robin by NPW/8 warp groups (more warps in flight without growing the stage).
+  static constexpr int kKsPerStage = NPW > 12 ? 8 : NPW;
+  static constexpr int kGroups = NPW / kKsPerStage;
   static constexpr int kStageB = kKsPerStage * kKsB;
   static constexpr int kStageA = kKsPerStage * kKsA;
   static constexpr int kStagesPerChunk = 4;             // metadata chunk = 4 stages
@@ -71,7 +74,7 @@ constexpr size_t tc_smem_bytes() {
   using G = TcGeom<NPW>;
   constexpr int S = KSTEPS / G::kKsPerStage;
   return size_t(S) * (G::kStageB + G::kStageA) + size_t(G::kMetaSlots) * (G::kMetaH + G::kMetaP) +
-         (2 * S + 2 * G::kMetaSlots + 4) * 8 + 16 + 1024 /*align slack*/;
+         (2 * S + 2 * G::kMetaSlots + 4) * 8 + 16 + 128 /*nibble table*/ + 1024 /*align slack*/;
 }
 
 template <typename T, int KSTEPS, int NPW>
@@ -81,7 +84,9 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
                   const int4 *__restrict__ hind4, int32_t num_nodes, int32_t N, float *__restrict__ C,
                   float *__restrict__ scratch) {
   using G = TcGeom<NPW>;
-  static_assert(KSTEPS >= 2 * NPW && KSTEPS % NPW == 0, "KSTEPS must be a multiple of NPW, at least 2 stages");
+  static_assert(NPW % G::kKsPerStage == 0, "producer warps must form whole groups");
+  static_assert(KSTEPS % G::kKsPerStage == 0 && KSTEPS / G::kKsPerStage > G::kGroups,
+                "the ring must hold more stages than there are producer groups");
   constexpr uint32_t S = KSTEPS / G::kKsPerStage;
   constexpr uint32_t MR = G::kMetaSlots;
   extern __shared__ uint8_t smem_raw[];
@@ -92,6 +97,7 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
   const uint32_t sMetaP = sMetaH + MR * G::kMetaH;         // [MR][64 blocks][4 uint32]
   const uint32_t sBar = sMetaP + MR * G::kMetaP;           // full[S] empty[S] mfull[MR] mempty[MR] tfull[2] tempty[2]
   const uint32_t sTmem = sBar + (2 * S + 2 * MR + 4) * 8;
+  const uint32_t sLut = sTmem + 16;                        // [16] nibble -> four 16-bit {0, 1.0} values (8 B each)
   auto full_bar = [&](uint32_t s) { return sBar + s * 8; };
   auto empty_bar = [&](uint32_t s) { return sBar + (S + s) * 8; };
   auto mfull_bar = [&](uint32_t m) { return sBar + (2 * S + m) * 8; };
@@ -120,7 +126,7 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
       }
       for (uint32_t m = 0; m < MR; ++m) {
         ptx::mbar_init(mfull_bar(m), 1);               // loader's arrive.expect_tx
-        ptx::mbar_init(mempty_bar(m), G::kKsPerStage); // one arrive per producer warp
+        ptx::mbar_init(mempty_bar(m), NPW);            // one arrive per producer warp
       }
       for (uint32_t a = 0; a < 2; ++a) {
         ptx::mbar_init(tfull_bar(a), 1);               // tcgen05.commit after the item's last MMA
@@ -131,7 +137,15 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
     __syncwarp();
     ptx::tmem_alloc<G::kTmemCols>(sTmem);
   }
-  if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&tmap);
+  if (warp == 0) {
+    if (lane == 0) ptx::prefetch_tensormap(&tmap);
+    if (lane < 16) {
+      constexpr uint32_t one = TcFmt<T>::kOne;
+      const uint32_t w0 = ((lane & 1) ? one : 0u) | ((lane & 2) ? (one << 16) : 0u);
+      const uint32_t w1 = ((lane & 4) ? one : 0u) | ((lane & 8) ? (one << 16) : 0u);
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sLut + lane * 8), "r"(w0), "r"(w1) : "memory");
+    }
+  }
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -141,6 +155,7 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
   if (warp == G::kLoaderWarp) {
     // ------------------------------------------------------------------ metadata loader (one lane)
     if (ptx::elect_one()) {
+      const uint64_t pol = ptx::policy_evict_first();   // hind / bitmaps are streamed once: do not displace B in L2
       uint32_t gc = 0;
       for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
         const WorkItem it = load_item(u / n_feat_tiles);
@@ -149,61 +164,63 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
           const uint32_t nb = uint32_t(min(G::kChunkBlks, it.blk_count - b0));
           ptx::mbar_wait(mempty_bar(m), ((gc / MR) & 1u) ^ 1u);
           ptx::mbar_arrive_expect_tx(mfull_bar(m), nb * 48u);
-          ptx::bulk_g2s(sMetaH + m * G::kMetaH, hind4 + int64_t(it.blk_begin + b0) * 2, nb * 32u, mfull_bar(m));
-          ptx::bulk_g2s(sMetaP + m * G::kMetaP, packed + int64_t(it.blk_begin + b0), nb * 16u, mfull_bar(m));
+          ptx::bulk_g2s_hint(sMetaH + m * G::kMetaH, hind4 + int64_t(it.blk_begin + b0) * 2, nb * 32u, mfull_bar(m), pol);
+          ptx::bulk_g2s_hint(sMetaP + m * G::kMetaP, packed + int64_t(it.blk_begin + b0), nb * 16u, mfull_bar(m), pol);
         }
       }
     }
-  } else if (warp < G::kKsPerStage) {
+  } else if (warp < NPW) {
     // ------------------------------------------------------------------ producers: bitmap expansion + TMA gather
+    // Ring / chunk positions are carried incrementally (no div / mod in the loop); the common K-step (both TC
+    // blocks present, both feature halves) runs a select-free path.
     const int n = lane & 15;     // window row
     const int kc = lane >> 4;    // which TC block of the K-step (= which 8-column chunk of K)
-    const uint32_t a_off = uint32_t(warp) * G::kKsA + (n >> 3) * 256 + kc * 128 + (n & 7) * 16;
-    const uint32_t word_off = uint32_t(n >> 3) * 4, shift = uint32_t(n & 7) << 2;
-    constexpr uint32_t one = TcFmt<T>::kOne;
-    uint32_t gs = 0, gc = 0;
+    const int kw = warp % G::kKsPerStage;   // this warp's K-step within a stage
+    const int grp = warp / G::kKsPerStage;  // stages st with st % kGroups == grp are this warp's
+    const uint32_t a_off = uint32_t(kw) * G::kKsA + (n >> 3) * 256 + kc * 128 + (n & 7) * 16;
+    const uint32_t p_off = uint32_t(2 * kw + kc) * 16 + uint32_t(n >> 3) * 4, shift = uint32_t(n & 7) << 2;
+    uint32_t s = 0, par = 0, m = 0, mpar = 0;
+    int32_t turn = 0;                       // global stage counter mod kGroups
     for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
       const WorkItem it = load_item(u / n_feat_tiles);
       const int32_t c_base = (u % n_feat_tiles) * G::kFeatTile;
-      const int32_t nj = min(2, (N - c_base + G::kAtomCols - 1) / G::kAtomCols);
+      const int32_t c1 = c_base + G::kAtomCols;
+      const bool two_halves = c1 < N;
       const int32_t nks = (it.blk_count + 1) >> 1;
       const int32_t nst = (nks + G::kKsPerStage - 1) / G::kKsPerStage;
-      for (int32_t st = 0; st < nst; ++st, ++gs) {
-        const uint32_t s = gs % S, par = (gs / S) & 1u;
-        const int32_t cst = st % G::kStagesPerChunk;         // stage within its metadata chunk
-        const uint32_t m = (gc + uint32_t(st / G::kStagesPerChunk)) % MR;
-        if (cst == 0) ptx::mbar_wait(mfull_bar(m), ((gc + uint32_t(st / G::kStagesPerChunk)) / MR) & 1u);
-        const int32_t ks = st * G::kKsPerStage + warp;
-        ptx::mbar_wait(empty_bar(s), par ^ 1u);
-        if (ks < nks) {
-          const int32_t lb = (cst * G::kKsPerStage + warp) * 2;           // first block of the K-step, chunk-local
-          const bool has_b1 = 2 * ks + 1 < it.blk_count;                  // odd block count: second half is empty
-          // A^T fragment of this lane: 8 K values (one TC block's 8 columns) of window row n
+      const int32_t full_ks = it.blk_count >> 1;    // K-steps with both TC blocks present
+      int32_t cst = 0, ks = kw;
+      for (int32_t st = 0; st < nst; ++st, ks += G::kKsPerStage) {
+        if (cst == 0) ptx::mbar_wait(mfull_bar(m), mpar);
+        const bool mine = G::kGroups == 1 || turn == grp;
+        if (G::kGroups > 1 && ++turn == G::kGroups) turn = 0;
+        const uint32_t bar = full_bar(s);
+        if (mine) ptx::mbar_wait(empty_bar(s), par ^ 1u);
+        if (!mine) {
+          // another group's stage: only the ring / chunk bookkeeping below
+        } else if (ks < nks) {
+          const uint32_t moff = uint32_t(cst) * (G::kKsPerStage * 2);   // first block of this stage, chunk-local
+          const uint32_t pa = sMetaP + m * G::kMetaP + moff * 16 + p_off;
+          const uint32_t ha = sMetaH + m * G::kMetaH + (moff + 2 * kw) * 32;
+          const uint32_t dst = sB + s * G::kStageB + uint32_t(kw) * G::kKsB;
+          const bool has_b1 = ks < full_ks;                 // odd block count: the item's last K-step is half empty
+          // A^T fragment of this lane: 8 K values (one TC block's 8 columns) of window row n, via the nibble table
           uint32_t lo = 0, hi = 0;
-          if (kc == 0 || has_b1) {
-            const uint32_t pa = sMetaP + m * G::kMetaP + uint32_t(lb + kc) * 16 + word_off;
-            lo = (ptx::lds32(pa) >> shift) & 0xfu;        // columns 0..3 of row n
-            hi = (ptx::lds32(pa + 8) >> shift) & 0xfu;    // columns 4..7
+          if (has_b1 || kc == 0) {
+            lo = (ptx::lds32(pa) >> shift) & 0xfu;          // columns 0..3 of row n
+            hi = (ptx::lds32(pa + 8) >> shift) & 0xfu;      // columns 4..7
           }
-          // two halves per word: bit i -> 16-bit 1.0 (no carries: the products occupy disjoint bit ranges)
-          const uint32_t v0 = ((lo & 1u) | ((lo & 2u) << 15)) * one, v1 = (((lo >> 2) & 1u) | ((lo & 8u) << 13)) * one;
-          const uint32_t v2 = ((hi & 1u) | ((hi & 2u) << 15)) * one, v3 = (((hi >> 2) & 1u) | ((hi & 8u) << 13)) * one;
-          ptx::sts128(sA + s * G::kStageA + a_off, v0, v1, v2, v3);
+          const uint2 e0 = ptx::lds64(sLut + lo * 8), e1 = ptx::lds64(sLut + hi * 8);
+          ptx::sts128(sA + s * G::kStageA + a_off, e0.x, e0.y, e1.x, e1.y);
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (ptx::elect_one()) {
-            const uint32_t ha = sMetaH + m * G::kMetaH + uint32_t(lb) * 32;
-            const int4 r0 = ptx::lds128(ha), r1 = ptx::lds128(ha + 16);
-            int4 r2 = make_int4(0, 0, 0, 0), r3 = make_int4(0, 0, 0, 0);   // tail: row 0, bitmap bits are 0
-            if (has_b1) { r2 = ptx::lds128(ha + 32); r3 = ptx::lds128(ha + 48); }
-            const uint32_t bar = full_bar(s);
-            ptx::mbar_arrive_expect_tx(bar, uint32_t(nj) * 2048u);
-            // atom (k-group kg, feature half j) sits at (kg*2 + j) * 1024; 4 rows = half an atom (512 B)
-            const uint32_t dst = sB + s * G::kStageB + uint32_t(warp) * G::kKsB;
-            // issued row-group-major so the 4 row coordinates of a group stay in place in the uniform registers
-            // and only destination / column change between the two feature halves
-            if (nj == 2) {
-              const int32_t c1 = c_base + G::kAtomCols;
+            // atom (k-group kg, feature half j) sits at (kg*2 + j) * 1024; 4 rows = half an atom (512 B);
+            // issued row-group-major so a group's 4 row coordinates are converted to uniform registers once
+            if (has_b1 && two_halves) {
+              const int4 r0 = ptx::lds128(ha), r1 = ptx::lds128(ha + 16), r2 = ptx::lds128(ha + 32),
+                         r3 = ptx::lds128(ha + 48);
+              ptx::mbar_arrive_expect_tx(bar, 4096u);
               ptx::tma_gather4(dst, &tmap, bar, c_base, r0.x, r0.y, r0.z, r0.w);
               ptx::tma_gather4(dst + 1024, &tmap, bar, c1, r0.x, r0.y, r0.z, r0.w);
               ptx::tma_gather4(dst + 512, &tmap, bar, c_base, r1.x, r1.y, r1.z, r1.w);
@@ -213,26 +230,40 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
               ptx::tma_gather4(dst + 2560, &tmap, bar, c_base, r3.x, r3.y, r3.z, r3.w);
               ptx::tma_gather4(dst + 3584, &tmap, bar, c1, r3.x, r3.y, r3.z, r3.w);
             } else {
+              const int4 r0 = ptx::lds128(ha), r1 = ptx::lds128(ha + 16);
+              int4 r2 = make_int4(0, 0, 0, 0), r3 = make_int4(0, 0, 0, 0);   // tail: row 0, bitmap bits are 0
+              if (has_b1) { r2 = ptx::lds128(ha + 32); r3 = ptx::lds128(ha + 48); }
+              ptx::mbar_arrive_expect_tx(bar, two_halves ? 4096u : 2048u);
               ptx::tma_gather4(dst, &tmap, bar, c_base, r0.x, r0.y, r0.z, r0.w);
               ptx::tma_gather4(dst + 512, &tmap, bar, c_base, r1.x, r1.y, r1.z, r1.w);
               ptx::tma_gather4(dst + 2048, &tmap, bar, c_base, r2.x, r2.y, r2.z, r2.w);
               ptx::tma_gather4(dst + 2560, &tmap, bar, c_base, r3.x, r3.y, r3.z, r3.w);
+              if (two_halves) {
+                ptx::tma_gather4(dst + 1024, &tmap, bar, c1, r0.x, r0.y, r0.z, r0.w);
+                ptx::tma_gather4(dst + 1536, &tmap, bar, c1, r1.x, r1.y, r1.z, r1.w);
+                ptx::tma_gather4(dst + 3072, &tmap, bar, c1, r2.x, r2.y, r2.z, r2.w);
+                ptx::tma_gather4(dst + 3584, &tmap, bar, c1, r3.x, r3.y, r3.z, r3.w);
+              }
             }
           }
         } else if (lane == 0) {
-          ptx::mbar_arrive(full_bar(s));   // K-step past the item's end: nothing to load, keep the count
+          ptx::mbar_arrive(bar);   // K-step past the item's end: nothing to load, keep the arrival count
         }
+        if (++s == S) { s = 0; par ^= 1u; }
         if (cst == G::kStagesPerChunk - 1 || st == nst - 1) {   // done with this metadata chunk
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(mempty_bar(m));
+          cst = 0;
+          if (++m == MR) { m = 0; mpar ^= 1u; }
+        } else {
+          ++cst;
         }
       }
-      gc += uint32_t((it.blk_count + G::kChunkBlks - 1) / G::kChunkBlks);
     }
   } else if (warp == G::kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = ptx::make_idesc(TcFmt<T>::kFmt, /*A MN-major*/ true, /*B K-major*/ false, 128, 16);
-    uint32_t gs = 0, unit = 0;
+    uint32_t s = 0, par = 0, unit = 0;
     for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
       const WorkItem it = load_item(u / n_feat_tiles);
       const int32_t nks = (it.blk_count + 1) >> 1;
@@ -242,23 +273,34 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
       ptx::mbar_wait(tempty_bar(acc), ((unit >> 1) & 1u) ^ 1u);
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * 16;
-      for (int32_t st = 0; st < nst; ++st, ++gs) {
-        const uint32_t s = gs % S;
-        ptx::mbar_wait(full_bar(s), (gs / S) & 1u);
+      for (int32_t st = 0; st < nst; ++st) {
+        ptx::mbar_wait(full_bar(s), par);
         ptx::tc_fence_after_sync();
         if (ptx::elect_one()) {
           const int32_t kn = min(G::kKsPerStage, nks - st * G::kKsPerStage);
-          for (int32_t k = 0; k < kn; ++k) {
-            // A = gathered rows: MN-major SW128, LBO = feature-atom stride (1024), SBO = k-group stride (2048)
-            const uint64_t a_desc = ptx::smem_desc(sB + s * G::kStageB + k * G::kKsB, 1024, 2048, ptx::kLayoutSw128);
-            // B = densified tile: K-major, no swizzle, LBO = k-chunk stride (128), SBO = 8-row group stride (256)
-            const uint64_t b_desc = ptx::smem_desc(sA + s * G::kStageA + k * G::kKsA, 128, 256, ptx::kLayoutNone);
-            ptx::umma_f16(d_tmem, a_desc, b_desc, idesc, (st | k) > 0 ? 1u : 0u);
+          // A = gathered rows: MN-major SW128, LBO = feature-atom stride (1024), SBO = k-group stride (2048)
+          // B = densified tile: K-major, no swizzle, LBO = k-chunk stride (128), SBO = 8-row group stride (256)
+          // Only the 14-bit start-address field changes from K-step to K-step (+4096 B / +512 B, no carry out of
+          // the field: shared memory is < 256 KB), so the low words are advanced by constants.
+          const uint64_t a_desc = ptx::smem_desc(sB + s * G::kStageB, 1024, 2048, ptx::kLayoutSw128);
+          const uint64_t b_desc = ptx::smem_desc(sA + s * G::kStageA, 128, 256, ptx::kLayoutNone);
+          const uint32_t a_lo = uint32_t(a_desc), a_hi = uint32_t(a_desc >> 32);
+          const uint32_t b_lo = uint32_t(b_desc), b_hi = uint32_t(b_desc >> 32);
+          if (kn == G::kKsPerStage) {
+            ptx::umma_f16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, st > 0 ? 1u : 0u);
+#pragma unroll
+            for (int32_t k = 1; k < G::kKsPerStage; ++k)
+              ptx::umma_f16_split(d_tmem, a_lo + k * (G::kKsB >> 4), a_hi, b_lo + k * (G::kKsA >> 4), b_hi, idesc, 1u);
+          } else {
+            for (int32_t k = 0; k < kn; ++k)
+              ptx::umma_f16_split(d_tmem, a_lo + k * (G::kKsB >> 4), a_hi, b_lo + k * (G::kKsA >> 4), b_hi, idesc,
+                                  (st | k) > 0 ? 1u : 0u);
           }
           ptx::umma_commit(empty_bar(s));
           if (st == nst - 1) ptx::umma_commit(tfull_bar(acc));
         }
         __syncwarp();
+        if (++s == S) { s = 0; par ^= 1u; }
       }
       ++unit;
     }

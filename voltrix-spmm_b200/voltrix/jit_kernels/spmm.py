@@ -40,10 +40,10 @@ __return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}, {npw}>(
 _CTYPE = {torch.float32: "float", torch.float16: "__half", torch.bfloat16: "__nv_bfloat16"}
 
 # autotune space per input dtype: (model, stages)
-SPACE_HALF = ({"model": 0, "stages": 32, "npw": 8}, {"model": 0, "stages": 36, "npw": 12},
+SPACE_HALF = ({"model": 0, "stages": 36, "npw": 12}, {"model": 0, "stages": 40, "npw": 16}, {"model": 0, "stages": 40, "npw": 24},
               {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
 # variants reachable only through the explicit model=/stages= arguments (tests, scripts): prebuilt as well
-EXTRA_HALF = ({"model": 0, "stages": 16, "npw": 4},)
+EXTRA_HALF = ({"model": 0, "stages": 16, "npw": 4}, {"model": 0, "stages": 32, "npw": 8})
 SPACE_FP32 = ({"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
 
 
@@ -114,7 +114,7 @@ def spmm_kernel(
             int(input.shape[0]), current_stream())
 
     if model is not None:   # explicit variant (tests, benchmarks): a space of one, no timing runs
-        stages, npw = int(stages or 32), int(npw or {8: 4, 16: 4, 36: 12}.get(int(stages or 32), 8))
+        stages, npw = int(stages or 32), int(npw or {8: 4, 16: 4, 36: 12, 40: 16}.get(int(stages or 32), 8))
         space = ({"model": int(model), "stages": stages, "npw": npw},)
         keys = {"ctype": _CTYPE[input.dtype], "fixed": f"{model}/{stages}/{npw}"}
     else:
