@@ -33,6 +33,13 @@
 #include "voltrix/common.cuh"
 #include "voltrix/ptx.cuh"
 
+// Bottleneck-isolation builds (scripts/gpu_isolate.sh; results are garbage, timing only):
+//   VX_TC_DBG=1  producers + TMA gather run, the MMA issuer only commits      -> gather path alone
+//   VX_TC_DBG=2  bitmap expansion + MMAs run on stale shared memory, no TMA   -> MMA operand reads alone
+#ifndef VX_TC_DBG
+#define VX_TC_DBG 0
+#endif
+
 namespace voltrix {
 
 template <typename T> struct TcFmt;
@@ -214,7 +221,12 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
           ptx::sts128(sA + s * G::kStageA + a_off, e0.x, e0.y, e1.x, e1.y);
           ptx::fence_proxy_async_smem();
           __syncwarp();
+#if VX_TC_DBG == 2
+          if (lane == 0) ptx::mbar_arrive(bar);
+          if (false) {
+#else
           if (ptx::elect_one()) {
+#endif
             // atom (k-group kg, feature half j) sits at (kg*2 + j) * 1024; 4 rows = half an atom (512 B);
             // issued row-group-major so a group's 4 row coordinates are converted to uniform registers once
             if (has_b1 && two_halves) {
@@ -286,12 +298,16 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
           const uint64_t b_desc = ptx::smem_desc(sA + s * G::kStageA, 128, 256, ptx::kLayoutNone);
           const uint32_t a_lo = uint32_t(a_desc), a_hi = uint32_t(a_desc >> 32);
           const uint32_t b_lo = uint32_t(b_desc), b_hi = uint32_t(b_desc >> 32);
+#if VX_TC_DBG == 1
+          if (false) {
+#else
           if (kn == G::kKsPerStage) {
+#endif
             ptx::umma_f16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, st > 0 ? 1u : 0u);
 #pragma unroll
             for (int32_t k = 1; k < G::kKsPerStage; ++k)
               ptx::umma_f16_split(d_tmem, a_lo + k * (G::kKsB >> 4), a_hi, b_lo + k * (G::kKsA >> 4), b_hi, idesc, 1u);
-          } else {
+          } else if (VX_TC_DBG != 1) {
             for (int32_t k = 0; k < kn; ++k)
               ptx::umma_f16_split(d_tmem, a_lo + k * (G::kKsB >> 4), a_hi, b_lo + k * (G::kKsA >> 4), b_hi, idesc,
                                   (st | k) > 0 ? 1u : 0u);

@@ -136,6 +136,7 @@ def nvcc_flags() -> list:
     ]
     if PTXAS_VERBOSE_FLAG in os.environ:
         flags.append("--ptxas-options=-v")
+    flags += os.environ.get("VOLTRIX_EXTRA_NVCC_FLAGS", "").split()   # experiments; part of the cache key
     cxx_flags = ["-fPIC", "-O3", "-Wno-deprecated-declarations", "-Wno-abi", "-fno-gnu-unique"]
     return [*flags, f'--compiler-options={",".join(cxx_flags)}']
 
