@@ -3,4 +3,5 @@ from .spmm import (
     csr_preprocess,
     spmm,
     SpmmPlan,
+    HostStreamedSpMM,
 )

@@ -192,3 +192,68 @@ def spmm(
     )
 
     return output
+
+
+class HostStreamedSpMM:
+    """Extension for callers whose dense operand and result live in (pinned) HOST memory.
+
+    ``submit(feat_host, out_host)`` enqueues one SpMM: H2D copy of ``feat_host`` on a copy-in stream, the
+    kernel on a compute stream, D2H copy of the result on a copy-out stream, with double-buffered device
+    operands, so that the copies of step i+1 / i-1 overlap the kernel of step i (PCIe is full duplex and
+    the copy engines run beside the SMs).  ``wait()`` blocks until everything submitted has landed in host
+    memory.  All kernels run on ONE compute stream, in submission order: the K-split scratch of the plan is
+    never shared by two launches in flight.  The reference has no counterpart (its bench keeps operands on
+    the device, bench/bm_voltrix.py:15-26); every step still goes through ``spmm`` above.
+    """
+
+    def __init__(self, blk_offsets, hspa_packed, hind, num_nodes: int, num_edges: int, num_feats: int,
+                 dtype=torch.float16, input_rows: Optional[int] = None, depth: int = 2):
+        require_cuda()
+        dev = hspa_packed.device
+        self.state = (blk_offsets, hspa_packed, hind)
+        self.num_nodes, self.num_edges, self.depth = num_nodes, num_edges, depth
+        rows = input_rows if input_rows is not None else num_nodes
+        self.feat_dev = [torch.empty(rows, num_feats, dtype=dtype, device=dev) for _ in range(depth)]
+        self.out_dev = [torch.empty(num_nodes, num_feats, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]      # feat_dev[b] filled
+        self.ev_run = [torch.cuda.Event() for _ in range(depth)]     # kernel on buffers b finished
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]     # out_dev[b] copied out
+        self.count = 0
+        self.fork()
+
+    def fork(self, stream=None):
+        """Order everything submitted from now on after the work already queued on ``stream`` (default: current)."""
+        stream = stream if stream is not None else torch.cuda.current_stream(self.s_in.device)
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.wait_stream(stream)
+
+    def submit(self, feat_host: torch.Tensor, out_host: torch.Tensor):
+        b = self.count % self.depth
+        first_use = self.count < self.depth
+        with torch.cuda.stream(self.s_in):
+            if not first_use:
+                self.s_in.wait_event(self.ev_run[b])     # the kernel that read feat_dev[b] is done
+            self.feat_dev[b].copy_(feat_host, non_blocking=True)
+            self.ev_in[b].record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(self.ev_in[b])
+            if not first_use:
+                self.s_run.wait_event(self.ev_out[b])    # out_dev[b] has been copied out
+            spmm(*self.state, self.num_nodes, self.num_edges, self.feat_dev[b], out=self.out_dev[b])
+            self.ev_run[b].record(self.s_run)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_run[b])
+            out_host.copy_(self.out_dev[b], non_blocking=True)
+            self.ev_out[b].record(self.s_out)
+        self.count += 1
+
+    def join(self, stream=None):
+        """Make ``stream`` (default: the current stream) wait for everything submitted so far."""
+        stream = stream if stream is not None else torch.cuda.current_stream(self.s_in.device)
+        for s in (self.s_in, self.s_run, self.s_out):
+            stream.wait_stream(s)
+
+    def wait(self):
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.synchronize()
