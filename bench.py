@@ -61,6 +61,21 @@ def alg_bytes(nnz: int, M: int, K: int, N: int, in_bytes: int) -> int:
     return 4 * nnz + 4 * (M + 1) + K * N * in_bytes + M * N * 4
 
 
+def measured_traffic(tuned: dict, workload: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), if this run uses the
+    kernel variant and workload that capture was taken on; else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1b_traffic.json")) as f:
+            db = json.load(f)
+        for v in tuned.values():
+            key = f"vx_spmm_tc_kernel<__half,{v['stages']},{v['npw']}>|{workload}"
+            if v.get("model") == 0 and key in db:
+                return int(db[key]["dram_bytes_read"] + db[key]["dram_bytes_write"]), db[key]["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -341,10 +356,12 @@ def run_product_arm(args):
             flush.zero_()
             starts[i].record(); step(); ends[i].record()
         barrier(); t_wall = time.perf_counter() - t_wall
-        # keep the sampler alive over a burst without flushes so it sees the kernel under load
-        for _ in range(10):
-            step()
-        torch.cuda.synchronize()
+        # keep the sampler alive over ~1.5 s of back-to-back steps so nvidia-smi sees the kernel under load
+        t_end = time.perf_counter() + 1.5
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                step()
+            torch.cuda.synchronize()
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     ms = float(np.mean(step_ms))
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -409,6 +426,8 @@ def run_product_arm(args):
     abytes_local = 4 * sh.local_nnz + 4 * (sh.local_rows + 1) + M * N * 2 + sh.local_rows * N * 4
     achieved = abytes_local / (ms * 1e-3) / 1e9
     gather_bytes = (plan.total_blocks * 8 * N * 2 + 48 * plan.total_blocks + sh.local_rows * N * 4)
+    traffic, traffic_src = measured_traffic({k: v for k, v in tuned.items() if k[0] == "spmm_kernel"}, args.workload) \
+        if world == 1 and args.scale == 1.0 else (None, None)
     launches_per_step = 1 + (1 if plan.num_sparse_rows else 0) + (1 if plan.num_fixups else 0)
     line = {
         "metric": METRIC if N == 128 else METRIC.replace("N=128", f"N={N}"),
@@ -420,7 +439,7 @@ def run_product_arm(args):
                    "tuned": {str(k): v for k, v in tuned.items() if k[0] == "spmm_kernel"},
                    "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": abytes_local,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "alg_bytes_per_launch": abytes_local,
                      "alg_bytes_whole_job": abytes,
                      "gather_bytes_per_launch": gather_bytes, "gather_gbs": gather_bytes / (ms * 1e-3) / 1e9,
                      "note": "B (59.6 MB fp16) is L2-resident: the kernel is bound by the L2->SM gather stream "

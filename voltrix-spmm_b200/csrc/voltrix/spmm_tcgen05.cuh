@@ -39,6 +39,10 @@
 #ifndef VX_TC_DBG
 #define VX_TC_DBG 0
 #endif
+// Timing-only probes: 5 = producers skip the bitmap expansion (gather issue + loop bookkeeping only)
+#ifndef VX_TC_EXP
+#define VX_TC_EXP 0
+#endif
 
 namespace voltrix {
 
@@ -212,6 +216,7 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
           const uint32_t dst = sB + s * G::kStageB + uint32_t(kw) * G::kKsB;
           const bool has_b1 = ks < full_ks;                 // odd block count: the item's last K-step is half empty
           // A^T fragment of this lane: 8 K values (one TC block's 8 columns) of window row n, via the nibble table
+#if VX_TC_EXP != 5
           uint32_t lo = 0, hi = 0;
           if (has_b1 || kc == 0) {
             lo = (ptx::lds32(pa) >> shift) & 0xfu;          // columns 0..3 of row n
@@ -221,6 +226,7 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
           ptx::sts128(sA + s * G::kStageA + a_off, e0.x, e0.y, e1.x, e1.y);
           ptx::fence_proxy_async_smem();
           __syncwarp();
+#endif
 #if VX_TC_DBG == 2
           if (lane == 0) ptx::mbar_arrive(bar);
           if (false) {
