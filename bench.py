@@ -132,6 +132,7 @@ def cpu_baseline(indptr_h: np.ndarray, indices_h: np.ndarray, K: int, N: int, bu
     """Oracle C port (OpenMP, all host cores) on a bounded row sample of the same graph."""
     import oracle
     c = oracle.c()
+    c.set_num_threads(os.cpu_count() or 1)
     M = indptr_h.size - 1
     rng = np.random.default_rng(0)
     B = rng.random((K, N), dtype=np.float32)
@@ -262,6 +263,7 @@ def run_reference_arm(args):
     del indptr, indices
     import oracle
     c = oracle.c()
+    c.set_num_threads(os.cpu_count() or 1)     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     B = np.random.default_rng(0).random((M, N), dtype=np.float32)
     # bounded sample per step: ~ (budget / (steps + warmup)) seconds of CPU work
     per_step_s = max(1.0, 100.0 / (args.steps + args.warmup))
@@ -290,7 +292,7 @@ def run_reference_arm(args):
                              "note": "the reference ships no CPU SpMM; oracle/voltrix_oracle.c vo_spmm_csr (OpenMP)"},
             "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_product_arm(args):
@@ -470,12 +472,25 @@ def run_product_arm(args):
                 line["cpu_baseline"]["others"] = extra_cpu_baselines(ip_h, ix_h, M, N)
         except Exception as ex:
             line["cpu_baseline"] = {"error": str(ex)[:200]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
 
+def emit(line: dict):
+    """The ONE JSON line goes to the process's real stdout; everything else that writes to fd 1 while the bench runs
+    (NCCL prints its version banner there) has been redirected to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -86,6 +86,8 @@ class _COracle:
         L.vo_spmm_csr.argtypes = [_i32p, _i32p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
                                   _f32p, _f32p, ctypes.c_int]
         L.vo_num_threads.restype = ctypes.c_int
+        L.vo_set_num_threads.restype = None
+        L.vo_set_num_threads.argtypes = [ctypes.c_int]
 
     # -- a2: voltrix::preprocess (bmat_kernels.cuh:264-320) ------------------
     def preprocess(self, indptr: np.ndarray, indices: np.ndarray):
@@ -173,6 +175,9 @@ class _COracle:
 
     def num_threads(self) -> int:
         return int(self.lib.vo_num_threads())
+
+    def set_num_threads(self, n: int) -> None:
+        self.lib.vo_set_num_threads(int(n))
 
 
 class _RefLib:
