@@ -40,6 +40,7 @@ extern "C" {
 #define VX_MODEL_TCGEN05 0   /* tcgen05 + TMA gather4 persistent kernel (+ CUDA-core rows for sparse windows) */
 #define VX_MODEL_CSR_ROWS 1  /* CUDA-core, one warp per CSR row (needs plan CSR) */
 #define VX_MODEL_TILE_ROWS 2 /* CUDA-core, straight from the tile format */
+#define VX_MODEL_TCGEN05_F32 3 /* fp32 input on the tcgen05 path as two bf16 terms (hi + lo); needs plan->split_ws, stages 24 */
 
 int vx_abi_version(void);
 
@@ -104,6 +105,7 @@ typedef struct {
   const int32_t *sparse_rows;
   int32_t num_sparse_rows;
   int64_t input_rows;          /* rows of `input` (0 = num_nodes); > num_nodes for a row shard of A */
+  void *split_ws;              /* model 3 only: bf16 [input_rows][2 * embedding_dim] workspace (else NULL) */
 } vx_plan_t;
 
 int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind, int32_t num_nodes,

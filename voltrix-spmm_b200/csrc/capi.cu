@@ -25,6 +25,7 @@ static int spmm_dispatch(const int32_t *blk_offsets, const uint32_t *hspa_packed
   switch (stages) {
     case 8: VX_TC_VARIANT(8, 4);
     case 16: VX_TC_VARIANT(16, 4);
+    case 24: VX_TC_VARIANT(24, 8);
     case 36: VX_TC_VARIANT(36, 12);
     case 40: VX_TC_VARIANT(40, 16);
     case 41: VX_TC_VARIANT(40, 24);
@@ -35,7 +36,7 @@ static int spmm_dispatch(const int32_t *blk_offsets, const uint32_t *hspa_packed
 
 extern "C" {
 
-int vx_abi_version(void) { return 1; }
+int vx_abi_version(void) { return 2; }
 
 size_t vx_preprocess_workspace_bytes(int64_t num_edges, int32_t num_nodes) {
   return preprocess_workspace_bytes(num_edges, num_nodes);
@@ -118,6 +119,7 @@ int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32
     p.sparse_rows = plan->sparse_rows;
     p.num_sparse_rows = plan->num_sparse_rows;
     p.input_rows = plan->input_rows;
+    p.split_ws = plan->split_ws;
   }
   cudaStream_t s = (cudaStream_t)stream;
   switch (input_dtype) {

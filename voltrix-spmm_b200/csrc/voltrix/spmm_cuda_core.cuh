@@ -111,6 +111,42 @@ vx_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
   }
 }
 
+// Low-degree variant: one lane GROUP (LANES threads) per row, 32 / LANES rows per warp, no cross-group reduction.
+// With a mean degree of 2-10 (Yeast, DD, com-amazon ... in the C3 suite) a whole warp per row leaves most lane groups
+// without a non-zero; here every group walks its own row, 4 gathers deep.
+template <typename T, int LANES>
+__global__ void __launch_bounds__(256)
+vx_csr_subwarp_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                           const int32_t *__restrict__ row_list, int32_t num_rows, int32_t N,
+                           const T *__restrict__ B, float *__restrict__ C) {
+  constexpr int EPL = Vec16<T>::N;
+  constexpr int CHUNK = LANES * EPL;
+  const int32_t item = int32_t((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / LANES);
+  if (item >= num_rows) return;               // no warp-collective below: lanes may leave early
+  const int sub = threadIdx.x % LANES;
+  const int32_t row = row_list ? row_list[item] : item;
+  const int32_t f0 = blockIdx.y * CHUNK + sub * EPL;
+  if (f0 >= N) return;
+  const int32_t beg = indptr[row], end = indptr[row + 1];
+  float acc[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) acc[i] = 0.f;
+  const T *Bf = B + f0;
+  int32_t e = beg;
+  for (; e + 3 < end; e += 4) {
+    const int32_t c0 = __ldg(indices + e), c1 = __ldg(indices + e + 1), c2 = __ldg(indices + e + 2),
+                  c3 = __ldg(indices + e + 3);
+    const uint4 v0 = vx_ldg16(Bf + int64_t(c0) * N), v1 = vx_ldg16(Bf + int64_t(c1) * N);
+    const uint4 v2 = vx_ldg16(Bf + int64_t(c2) * N), v3 = vx_ldg16(Bf + int64_t(c3) * N);
+    Vec16<T>::add(acc, v0); Vec16<T>::add(acc, v1);
+    Vec16<T>::add(acc, v2); Vec16<T>::add(acc, v3);
+  }
+  for (; e < end; ++e) Vec16<T>::add(acc, vx_ldg16(Bf + int64_t(__ldg(indices + e)) * N));
+  float4 *dst = reinterpret_cast<float4 *>(C + int64_t(row) * N + f0);
+#pragma unroll
+  for (int i = 0; i < EPL / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+}
+
 // One warp per row of the tile format.  Lane l scans TC block (b0 + l) of the row's window for
 // its 8-bit column mask, then the warp walks the set bits together: every step all 32 lanes load
 // one 512-byte slice of one B row.
@@ -166,19 +202,30 @@ vx_tile_rows_kernel(const int32_t *__restrict__ blk_offsets, const uint32_t *__r
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+// mean_degree: non-zeros per row of the rows being computed (< 0 = unknown).  Rows with fewer non-zeros than a warp
+// has lane groups go to the group-per-row kernel; the choice depends only on (mean_degree, N), never on timing.
 template <typename T>
 inline int launch_csr_rows(const int32_t *indptr, const int32_t *indices, const int32_t *row_list, int32_t num_rows,
-                           int32_t N, const T *B, float *C, cudaStream_t stream) {
+                           int32_t N, const T *B, float *C, cudaStream_t stream, float mean_degree = -1.f) {
   constexpr int EPL = Vec16<T>::N;
   if (num_rows <= 0) return VX_OK;
   if (N <= 0 || N % EPL != 0) return VX_ERR_UNSUPPORTED;
   int lanes_needed = N / EPL;  // 16-byte loads per row
   dim3 block(256);
-  auto grid = [&](int lanes) { return dim3(ceil_div(num_rows, 8), ceil_div(N, lanes * EPL)); };
-  if (lanes_needed <= 4)       vx_csr_rows_kernel<T, 4><<<grid(4), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
-  else if (lanes_needed <= 8)  vx_csr_rows_kernel<T, 8><<<grid(8), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
-  else if (lanes_needed <= 16) vx_csr_rows_kernel<T, 16><<<grid(16), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
-  else                         vx_csr_rows_kernel<T, 32><<<grid(32), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+  const int lanes = lanes_needed <= 4 ? 4 : lanes_needed <= 8 ? 8 : lanes_needed <= 16 ? 16 : 32;
+  if (lanes < 32 && mean_degree >= 0.f && mean_degree < 4.f * float(32 / lanes)) {
+    dim3 g(unsigned(ceil_div<int64_t>(int64_t(num_rows) * lanes, 256)), ceil_div(N, lanes * EPL));
+    if (lanes == 4)      vx_csr_subwarp_rows_kernel<T, 4><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+    else if (lanes == 8) vx_csr_subwarp_rows_kernel<T, 8><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+    else                 vx_csr_subwarp_rows_kernel<T, 16><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+    VX_LAUNCH_CHECK();
+    return VX_OK;
+  }
+  auto grid = [&](int l) { return dim3(ceil_div(num_rows, 8), ceil_div(N, l * EPL)); };
+  if (lanes == 4)       vx_csr_rows_kernel<T, 4><<<grid(4), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+  else if (lanes == 8)  vx_csr_rows_kernel<T, 8><<<grid(8), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+  else if (lanes == 16) vx_csr_rows_kernel<T, 16><<<grid(16), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+  else                  vx_csr_rows_kernel<T, 32><<<grid(32), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
   VX_LAUNCH_CHECK();
   return VX_OK;
 }

@@ -9,10 +9,14 @@
 //            CUDA-core row kernel for the windows the schedule classified as sparse.
 //   model 1  CUDA-core CSR path for every row (needs the CSR arrays kept in the plan; exact fp32).
 //   model 2  CUDA-core path straight from the tile format (needs nothing but the reference triple).
+//   model 3  fp32 input on the tensor-core path: the operand is split into two bf16 terms (hi + lo, 16 mantissa
+//            bits -- the reference rounds to TF32's 10) in plan.split_ws, both terms accumulate into one TMEM tile.
 //
 // Unlike the reference, nothing here throws or calls exit(): errors come back as VX_* codes.
 #ifndef VOLTRIX_B200_SPMM_KERNELS_CUH_
 #define VOLTRIX_B200_SPMM_KERNELS_CUH_
+
+#include <type_traits>
 
 #include "voltrix/common.cuh"
 #include "voltrix/spmm_cuda_core.cuh"
@@ -33,6 +37,7 @@ struct SpmmPlan {
   int32_t num_sparse_rows = 0;
   int64_t input_rows = 0;                // rows of the dense operand (0 = num_nodes, i.e. square A);
                                          // differs for a row shard of A, whose columns span the full matrix
+  void *split_ws = nullptr;              // model 3: bf16 [input_rows][2 * embedding_dim] workspace
 };
 
 template <typename T> struct TcSupported { static constexpr bool value = false; };
@@ -43,7 +48,6 @@ template <typename T, int STAGES = 32, int NPW = 8>
 inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t *hspa_packed, const int32_t *hind,
                                      int num_nodes, int num_edges, int embedding_dim, const T *input, float *output,
                                      int model, const SpmmPlan &plan, cudaStream_t stream) {
-  (void)num_edges;
   if (num_nodes < 0 || embedding_dim <= 0) return VX_ERR_INVALID_ARG;
   if (num_nodes == 0) return VX_OK;
   const int32_t W = ceil_div<int32_t>(num_nodes, BLK_H);
@@ -73,9 +77,36 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
   } else if (model == 1) {
     if (!plan.csr_indptr || !plan.csr_indices) return VX_ERR_INVALID_ARG;
     return launch_csr_rows<T>(plan.csr_indptr, plan.csr_indices, nullptr, num_nodes, embedding_dim, input, output,
-                              stream);
+                              stream, float(num_edges) / float(num_nodes));
   } else if (model == 2) {
     return launch_tile_rows<T>(blks_offsets, hspa_packed, hind, num_nodes, embedding_dim, input, output, stream);
+  } else if (model == 3) {
+    if constexpr (std::is_same<T, float>::value && tc_smem_bytes<STAGES, NPW, 2>() <= 227 * 1024) {
+      if (plan.split_ws == nullptr) return VX_ERR_INVALID_ARG;
+      if (embedding_dim % 8 != 0) return VX_ERR_UNSUPPORTED;
+      if (plan.num_fixups > 0 && plan.scratch == nullptr) return VX_ERR_INVALID_ARG;
+      __nv_bfloat16 *terms = static_cast<__nv_bfloat16 *>(plan.split_ws);
+      int rc = launch_split_bf16x2(input, terms, b_rows, embedding_dim, stream);
+      if (rc != VX_OK) return rc;
+      if (plan.items != nullptr) {
+        rc = launch_spmm_tc<__nv_bfloat16, STAGES, NPW, 2>(plan.items, plan.num_items, plan.fixups, plan.num_fixups,
+                                                           blks_offsets, hspa_packed, hind, num_nodes, b_rows,
+                                                           embedding_dim, terms, output, plan.scratch, stream);
+        if (rc != VX_OK) return rc;
+        if (plan.num_sparse_rows > 0) {   // sparse windows: exact fp32 rows from the original operand
+          if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows) return VX_ERR_INVALID_ARG;
+          rc = launch_csr_rows<T>(plan.csr_indptr, plan.csr_indices, plan.sparse_rows, plan.num_sparse_rows,
+                                  embedding_dim, input, output, stream);
+        }
+      } else {
+        rc = launch_spmm_tc<__nv_bfloat16, STAGES, NPW, 2>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind,
+                                                           num_nodes, b_rows, embedding_dim, terms, output, nullptr,
+                                                           stream);
+      }
+      return rc;
+    } else {
+      return VX_ERR_UNSUPPORTED;
+    }
   }
   return VX_ERR_INVALID_ARG;
 }

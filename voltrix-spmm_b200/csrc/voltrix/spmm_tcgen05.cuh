@@ -56,11 +56,16 @@ template <> struct TcFmt<__nv_bfloat16> {
   static constexpr CUtensorMapDataType kTmapType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 };
 
-template <int NPW>
+// TERMS: the dense operand is stored as TERMS 16-bit terms per value (column blocks of `term_stride` elements in the
+// tensor map) whose products accumulate into the same TMEM tile.  TERMS = 1 for fp16 / bf16 input; TERMS = 2 is the fp32
+// path: x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits, full fp32 exponent range; the reference
+// rounds fp32 to TF32 = 10 mantissa bits, spmm_kernels.cuh:1631-1678).
+template <int NPW, int TERMS = 1>
 struct TcGeom {
   static constexpr int kFeatTile = 128;                 // MMA M: features per work unit
   static constexpr int kAtomCols = 64;                  // 128-byte swizzle span in 16-bit elements
-  static constexpr int kKsB = kFeatTile * 16 * 2;       // one K-step: 16 gathered rows x 128 features x 2 B = 4096
+  static constexpr int kTermB = kFeatTile * 16 * 2;     // one term of one K-step: 16 gathered rows x 128 features x 2 B = 4096
+  static constexpr int kKsB = kTermB * TERMS;           // one K-step, all terms
   static constexpr int kKsA = 16 * 16 * 2;              // one K-step: densified 16 x 16 tile = 512
   // K-steps per stage.  Up to 12 producer warps: one stage = one K-step per warp.  More warps: stages of 8
   // K-steps owned round-robin by NPW/8 warp groups (more warps in flight without growing the stage).
@@ -80,21 +85,21 @@ struct TcGeom {
 };
 
 // KSTEPS = K-steps in flight (the autotuned "stages" knob): ring depth = KSTEPS / NPW stages.
-template <int KSTEPS, int NPW>
+template <int KSTEPS, int NPW, int TERMS = 1>
 constexpr size_t tc_smem_bytes() {
-  using G = TcGeom<NPW>;
+  using G = TcGeom<NPW, TERMS>;
   constexpr int S = KSTEPS / G::kKsPerStage;
   return size_t(S) * (G::kStageB + G::kStageA) + size_t(G::kMetaSlots) * (G::kMetaH + G::kMetaP) +
          (2 * S + 2 * G::kMetaSlots + 4) * 8 + 16 + 128 /*nibble table*/ + 1024 /*align slack*/;
 }
 
-template <typename T, int KSTEPS, int NPW>
-__global__ void __launch_bounds__(TcGeom<NPW>::kThreads, 1)
+template <typename T, int KSTEPS, int NPW, int TERMS = 1>
+__global__ void __launch_bounds__(TcGeom<NPW, TERMS>::kThreads, 1)
 vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__restrict__ items, int32_t num_items,
                   int32_t n_feat_tiles, const int32_t *__restrict__ blk_offsets, const uint4 *__restrict__ packed,
                   const int4 *__restrict__ hind4, int32_t num_nodes, int32_t N, float *__restrict__ C,
-                  float *__restrict__ scratch) {
-  using G = TcGeom<NPW>;
+                  float *__restrict__ scratch, int32_t term_stride) {
+  using G = TcGeom<NPW, TERMS>;
   static_assert(NPW % G::kKsPerStage == 0, "producer warps must form whole groups");
   static_assert(KSTEPS % G::kKsPerStage == 0 && KSTEPS / G::kKsPerStage > G::kGroups,
                 "the ring must hold more stages than there are producer groups");
@@ -238,29 +243,39 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
             if (has_b1 && two_halves) {
               const int4 r0 = ptx::lds128(ha), r1 = ptx::lds128(ha + 16), r2 = ptx::lds128(ha + 32),
                          r3 = ptx::lds128(ha + 48);
-              ptx::mbar_arrive_expect_tx(bar, 4096u);
-              ptx::tma_gather4(dst, &tmap, bar, c_base, r0.x, r0.y, r0.z, r0.w);
-              ptx::tma_gather4(dst + 1024, &tmap, bar, c1, r0.x, r0.y, r0.z, r0.w);
-              ptx::tma_gather4(dst + 512, &tmap, bar, c_base, r1.x, r1.y, r1.z, r1.w);
-              ptx::tma_gather4(dst + 1536, &tmap, bar, c1, r1.x, r1.y, r1.z, r1.w);
-              ptx::tma_gather4(dst + 2048, &tmap, bar, c_base, r2.x, r2.y, r2.z, r2.w);
-              ptx::tma_gather4(dst + 3072, &tmap, bar, c1, r2.x, r2.y, r2.z, r2.w);
-              ptx::tma_gather4(dst + 2560, &tmap, bar, c_base, r3.x, r3.y, r3.z, r3.w);
-              ptx::tma_gather4(dst + 3584, &tmap, bar, c1, r3.x, r3.y, r3.z, r3.w);
+              ptx::mbar_arrive_expect_tx(bar, uint32_t(G::kKsB));
+#pragma unroll
+              for (int t = 0; t < TERMS; ++t) {   // term t: columns shifted by t * term_stride, tile t of the K-step
+                const uint32_t d = dst + t * G::kTermB;
+                const int32_t ca = c_base + t * term_stride, cb = c1 + t * term_stride;
+                ptx::tma_gather4(d, &tmap, bar, ca, r0.x, r0.y, r0.z, r0.w);
+                ptx::tma_gather4(d + 1024, &tmap, bar, cb, r0.x, r0.y, r0.z, r0.w);
+                ptx::tma_gather4(d + 512, &tmap, bar, ca, r1.x, r1.y, r1.z, r1.w);
+                ptx::tma_gather4(d + 1536, &tmap, bar, cb, r1.x, r1.y, r1.z, r1.w);
+                ptx::tma_gather4(d + 2048, &tmap, bar, ca, r2.x, r2.y, r2.z, r2.w);
+                ptx::tma_gather4(d + 3072, &tmap, bar, cb, r2.x, r2.y, r2.z, r2.w);
+                ptx::tma_gather4(d + 2560, &tmap, bar, ca, r3.x, r3.y, r3.z, r3.w);
+                ptx::tma_gather4(d + 3584, &tmap, bar, cb, r3.x, r3.y, r3.z, r3.w);
+              }
             } else {
               const int4 r0 = ptx::lds128(ha), r1 = ptx::lds128(ha + 16);
               int4 r2 = make_int4(0, 0, 0, 0), r3 = make_int4(0, 0, 0, 0);   // tail: row 0, bitmap bits are 0
               if (has_b1) { r2 = ptx::lds128(ha + 32); r3 = ptx::lds128(ha + 48); }
-              ptx::mbar_arrive_expect_tx(bar, two_halves ? 4096u : 2048u);
-              ptx::tma_gather4(dst, &tmap, bar, c_base, r0.x, r0.y, r0.z, r0.w);
-              ptx::tma_gather4(dst + 512, &tmap, bar, c_base, r1.x, r1.y, r1.z, r1.w);
-              ptx::tma_gather4(dst + 2048, &tmap, bar, c_base, r2.x, r2.y, r2.z, r2.w);
-              ptx::tma_gather4(dst + 2560, &tmap, bar, c_base, r3.x, r3.y, r3.z, r3.w);
-              if (two_halves) {
-                ptx::tma_gather4(dst + 1024, &tmap, bar, c1, r0.x, r0.y, r0.z, r0.w);
-                ptx::tma_gather4(dst + 1536, &tmap, bar, c1, r1.x, r1.y, r1.z, r1.w);
-                ptx::tma_gather4(dst + 3072, &tmap, bar, c1, r2.x, r2.y, r2.z, r2.w);
-                ptx::tma_gather4(dst + 3584, &tmap, bar, c1, r3.x, r3.y, r3.z, r3.w);
+              ptx::mbar_arrive_expect_tx(bar, uint32_t(two_halves ? G::kKsB : G::kKsB / 2));
+#pragma unroll
+              for (int t = 0; t < TERMS; ++t) {
+                const uint32_t d = dst + t * G::kTermB;
+                const int32_t ca = c_base + t * term_stride, cb = c1 + t * term_stride;
+                ptx::tma_gather4(d, &tmap, bar, ca, r0.x, r0.y, r0.z, r0.w);
+                ptx::tma_gather4(d + 512, &tmap, bar, ca, r1.x, r1.y, r1.z, r1.w);
+                ptx::tma_gather4(d + 2048, &tmap, bar, ca, r2.x, r2.y, r2.z, r2.w);
+                ptx::tma_gather4(d + 2560, &tmap, bar, ca, r3.x, r3.y, r3.z, r3.w);
+                if (two_halves) {
+                  ptx::tma_gather4(d + 1024, &tmap, bar, cb, r0.x, r0.y, r0.z, r0.w);
+                  ptx::tma_gather4(d + 1536, &tmap, bar, cb, r1.x, r1.y, r1.z, r1.w);
+                  ptx::tma_gather4(d + 3072, &tmap, bar, cb, r2.x, r2.y, r2.z, r2.w);
+                  ptx::tma_gather4(d + 3584, &tmap, bar, cb, r3.x, r3.y, r3.z, r3.w);
+                }
               }
             }
           }
@@ -309,14 +324,18 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
 #else
           if (kn == G::kKsPerStage) {
 #endif
-            ptx::umma_f16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, st > 0 ? 1u : 0u);
 #pragma unroll
-            for (int32_t k = 1; k < G::kKsPerStage; ++k)
-              ptx::umma_f16_split(d_tmem, a_lo + k * (G::kKsB >> 4), a_hi, b_lo + k * (G::kKsA >> 4), b_hi, idesc, 1u);
+            for (int32_t k = 0; k < G::kKsPerStage; ++k)
+#pragma unroll
+              for (int32_t t = 0; t < TERMS; ++t)   // every term of the K-step multiplies the same densified tile
+                ptx::umma_f16_split(d_tmem, a_lo + ((k * G::kKsB + t * G::kTermB) >> 4), a_hi, b_lo + k * (G::kKsA >> 4),
+                                    b_hi, idesc, (k | t) > 0 ? 1u : (st > 0 ? 1u : 0u));
           } else if (VX_TC_DBG != 1) {
             for (int32_t k = 0; k < kn; ++k)
-              ptx::umma_f16_split(d_tmem, a_lo + k * (G::kKsB >> 4), a_hi, b_lo + k * (G::kKsA >> 4), b_hi, idesc,
-                                  (st | k) > 0 ? 1u : 0u);
+#pragma unroll
+              for (int32_t t = 0; t < TERMS; ++t)
+                ptx::umma_f16_split(d_tmem, a_lo + ((k * G::kKsB + t * G::kTermB) >> 4), a_hi, b_lo + k * (G::kKsA >> 4),
+                                    b_hi, idesc, (st | k | t) > 0 ? 1u : 0u);
           }
           ptx::umma_commit(empty_bar(s));
           if (st == nst - 1) ptx::umma_commit(tfull_bar(acc));
@@ -407,7 +426,7 @@ inline PFN_vxTensorMapEncodeTiled get_tensor_map_encoder() {
 
 // 2-D map over B[rows, N] whose box is one 128-byte row segment: the shape tile::gather4 needs.
 inline int make_gather_tensor_map(CUtensorMap *out, const void *B, CUtensorMapDataType dt, int elem_bytes,
-                                  int64_t rows, int32_t N) {
+                                  int64_t rows, int64_t N) {
   PFN_vxTensorMapEncodeTiled enc = get_tensor_map_encoder();
   if (!enc) return VX_ERR_CUDA;
   cuuint64_t gdim[2] = {cuuint64_t(N), cuuint64_t(rows)};
@@ -436,7 +455,8 @@ inline int device_sm_count() {
 
 // Launch the tensor-core kernel over a prepared work list.  B must be 16-byte aligned with N % 8 == 0
 // (TMA global-stride rule); hind / hspa_packed must be 16-byte aligned.
-template <typename T, int STAGES, int NPW>
+// `B` holds TERMS column blocks of N elements per row (row stride TERMS * N): plain fp16 / bf16 input has TERMS = 1.
+template <typename T, int STAGES, int NPW, int TERMS = 1>
 inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupItem *fixups, int32_t num_fixups,
                           const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind,
                           int32_t num_nodes, int64_t b_rows,
@@ -446,11 +466,11 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
       (reinterpret_cast<uintptr_t>(hspa_packed) & 15))
     return VX_ERR_UNSUPPORTED;
   CUtensorMap tmap;
-  int rc = make_gather_tensor_map(&tmap, B, TcFmt<T>::kTmapType, 2, b_rows, N);
+  int rc = make_gather_tensor_map(&tmap, B, TcFmt<T>::kTmapType, 2, b_rows, int64_t(N) * TERMS);
   if (rc != VX_OK) return rc;
-  using G = TcGeom<NPW>;
-  auto kern = vx_spmm_tc_kernel<T, STAGES, NPW>;
-  constexpr size_t smem = tc_smem_bytes<STAGES, NPW>();
+  using G = TcGeom<NPW, TERMS>;
+  auto kern = vx_spmm_tc_kernel<T, STAGES, NPW, TERMS>;
+  constexpr size_t smem = tc_smem_bytes<STAGES, NPW, TERMS>();
   static_assert(smem <= 227 * 1024, "stage ring does not fit in shared memory");
   // Set on every launch (~1 us): a function-local `static bool` would be a GNU_UNIQUE symbol shared by every
   // JIT artefact / library that instantiates this template, while each of them owns a distinct kernel copy.
@@ -460,12 +480,44 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
   const int grid = int(total_units < device_sm_count() ? total_units : device_sm_count());
   kern<<<grid, G::kThreads, smem, stream>>>(tmap, items, num_items, n_feat_tiles, blk_offsets,
                                                  reinterpret_cast<const uint4 *>(hspa_packed),
-                                                 reinterpret_cast<const int4 *>(hind), num_nodes, N, C, scratch);
+                                                 reinterpret_cast<const int4 *>(hind), num_nodes, N, C, scratch, N);
   VX_LAUNCH_CHECK();
   if (num_fixups > 0) {
     vx_fixup_kernel<<<num_fixups, 256, 0, stream>>>(fixups, num_fixups, scratch, num_nodes, N, C);
     VX_LAUNCH_CHECK();
   }
+  return VX_OK;
+}
+
+// fp32 -> [hi | lo] bf16 terms: out[r, c] = bf16(x), out[r, N + c] = bf16(x - hi).  One thread per 4 values.
+__global__ void vx_split_bf16x2_kernel(const float4 *__restrict__ in, __nv_bfloat16 *__restrict__ out, int64_t rows,
+                                       int32_t N) {
+  const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;   // quad index
+  const int32_t qpr = N >> 2;
+  if (q >= rows * qpr) return;
+  const int64_t r = q / qpr;
+  const int32_t c = int32_t(q - r * qpr) << 2;
+  const float4 v = in[q];
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = __float2bfloat16_rn(x[i]);
+    lo[i] = __float2bfloat16_rn(x[i] - __bfloat162float(hi[i]));
+  }
+  __nv_bfloat16 *o = out + r * (2 * int64_t(N)) + c;
+  *reinterpret_cast<uint2 *>(o) = *reinterpret_cast<const uint2 *>(hi);
+  *reinterpret_cast<uint2 *>(o + N) = *reinterpret_cast<const uint2 *>(lo);
+}
+
+inline int launch_split_bf16x2(const float *in, __nv_bfloat16 *out, int64_t rows, int32_t N, cudaStream_t stream) {
+  if (N % 4 != 0 || (reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7))
+    return VX_ERR_UNSUPPORTED;
+  const int64_t quads = rows * (N >> 2);
+  if (quads <= 0) return VX_OK;
+  vx_split_bf16x2_kernel<<<unsigned((quads + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4 *>(in), out,
+                                                                            rows, N);
+  VX_LAUNCH_CHECK();
   return VX_OK;
 }
 

@@ -32,6 +32,7 @@ plan.csr_indices = csr_indices;
 plan.sparse_rows = sparse_rows;
 plan.num_sparse_rows = num_sparse_rows;
 plan.input_rows = input_rows;
+plan.split_ws = split_ws;
 __return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}, {npw}>(
     blk_offsets, hspa_packed, hind,
     num_nodes, num_edges, embedding_dim, input, output, {model}, plan, stream);
@@ -44,7 +45,8 @@ SPACE_HALF = ({"model": 0, "stages": 36, "npw": 12}, {"model": 0, "stages": 40, 
               {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
 # variants reachable only through the explicit model=/stages= arguments (tests, scripts): prebuilt as well
 EXTRA_HALF = ({"model": 0, "stages": 16, "npw": 4}, {"model": 0, "stages": 32, "npw": 8})
-SPACE_FP32 = ({"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
+# fp32: model 3 = tcgen05 on two bf16 terms (hi + lo); models 1 / 2 = exact-fp32 CUDA-core rows
+SPACE_FP32 = ({"model": 3, "stages": 24, "npw": 8}, {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
 
 
 def arg_defs_for(dtype):
@@ -67,8 +69,27 @@ def arg_defs_for(dtype):
         ("sparse_rows", torch.int32),
         ("num_sparse_rows", int),
         ("input_rows", int),
+        ("split_ws", torch.bfloat16),
         ("stream", torch.cuda.Stream),
     )
+
+
+def _split_workspace(owner, rows: int, embedding_dim: int, device) -> torch.Tensor:
+    """bf16 [rows, 2 * embedding_dim] buffer for the fp32 tensor-core path (model 3), cached on the plan (or on
+    ``hspa_packed`` when the caller came with a bare reference triple)."""
+    cache = getattr(owner, "_vx_split_ws", None)
+    if cache is None:
+        cache = {}
+        try:
+            owner._vx_split_ws = cache
+        except AttributeError:
+            pass
+    key = (rows, embedding_dim, str(device))
+    buf = cache.get(key)
+    if buf is None:
+        buf = torch.empty((rows, 2 * embedding_dim), dtype=torch.bfloat16, device=device)
+        cache[key] = buf
+    return buf
 
 
 def feature_hash(feature: torch.Tensor) -> str:
@@ -110,16 +131,27 @@ def spmm_kernel(
     if plan is None:
         plan = getattr(hspa_packed, "_vx_plan", None)
     p = plan.launch_args(embedding_dim) if plan is not None else (None, 0, None, 0, None, None, None, None, 0)
-    args = (blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, input, output, *p,
-            int(input.shape[0]), current_stream())
-
     if model is not None:   # explicit variant (tests, benchmarks): a space of one, no timing runs
-        stages, npw = int(stages or 32), int(npw or {8: 4, 16: 4, 36: 12, 40: 16}.get(int(stages or 32), 8))
+        stages = int(stages or (24 if int(model) == 3 else 32))
+        npw = int(npw or {8: 4, 16: 4, 36: 12, 40: 16}.get(stages, 8))
         space = ({"model": int(model), "stages": stages, "npw": npw},)
         keys = {"ctype": _CTYPE[input.dtype], "fixed": f"{model}/{stages}/{npw}"}
     else:
         space = SPACE_FP32 if input.dtype == torch.float32 else SPACE_HALF
         keys = {"ctype": _CTYPE[input.dtype], "feature_hash": feature_hash(hspa_packed), "N": embedding_dim}
+
+    # fp32 on the tensor cores (model 3) needs a bf16 [rows, 2N] workspace: hand it over while that model is still a
+    # candidate for this key, drop it once the tuner has settled on a CUDA-core model
+    signature = ("spmm_kernel", f"{ {k: keys[k] for k in sorted(keys)} }")
+    winner = jit_tuner.tuned_keys.get(signature)
+    ws_owner = plan if plan is not None else hspa_packed
+    split_ws = None
+    if input.dtype == torch.float32 and embedding_dim % 8 == 0 and any(c["model"] == 3 for c in space) and \
+            (winner is None or winner.get("model") == 3):
+        split_ws = _split_workspace(ws_owner, int(input.shape[0]), embedding_dim, input.device)
+    args = (blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, input, output, *p,
+            int(input.shape[0]), split_ws, current_stream())
+
     runtime = jit_tuner.compile_and_tune(
         name="spmm_kernel",
         keys=keys,
@@ -131,3 +163,5 @@ def spmm_kernel(
         kernel_tag="spmm",
     )
     check(runtime(*args), "spmm_kernel")
+    if split_ws is not None and jit_tuner.tuned_keys.get(signature, {}).get("model") != 3:
+        getattr(ws_owner, "_vx_split_ws", {}).clear()
