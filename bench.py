@@ -296,7 +296,10 @@ def run_reference_arm(args):
 
 
 def run_product_arm(args):
+    import faulthandler
     import torch.distributed as dist
+    # hang diagnosis: dump every thread's Python stack to stderr if the bench is still running after this long
+    faulthandler.dump_traceback_later(int(os.environ.get("VX_BENCH_STACK_DUMP_S", "900")), repeat=False, exit=False)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -304,8 +307,11 @@ def run_product_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        import datetime
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # a rank that stops making progress fails the collective after VX_BENCH_NCCL_TIMEOUT_S instead of 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(
+            seconds=int(os.environ.get("VX_BENCH_NCCL_TIMEOUT_S", "300"))))
     import voltrix
     from voltrix.distributed import ShardedSpMM
 
@@ -364,7 +370,10 @@ def run_product_arm(args):
             for _ in range(20):
                 step()
             torch.cuda.synchronize()
+    faulthandler.cancel_dump_traceback_later()
+    faulthandler.dump_traceback_later(int(os.environ.get("VX_BENCH_STACK_DUMP_S", "900")), repeat=False, exit=False)
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    log(f"[rank {rank}] timed loop done: {np.mean(step_ms):.3f} ms/step")
     ms = float(np.mean(step_ms))
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -375,45 +384,57 @@ def run_product_arm(args):
     # (a) serial: copy-in, voltrix.spmm, copy-out on one stream.  (b) streamed: voltrix.HostStreamedSpMM runs the
     # same three legs of consecutive steps on three streams (double-buffered), so PCIe in, the kernel and PCIe out
     # overlap; every step still moves its own B and its own C.  The reported e2e value is (b).
-    feat_host = feat.cpu().pin_memory()
-    out_host = [torch.empty(sh.local_rows, N, dtype=torch.float32).pin_memory() for _ in range(2)]
-    feat_dev = torch.empty_like(feat)
+    # Rank-INVARIANT decision (every rank must take the same branch: the legs below contain barriers): every rank pins a
+    # full copy of B plus two buffers for its shard of C; on the 1B-nnz R-MAT that is 17 GB x 8 of page-locked memory.
+    e2e_bytes = world * M * N * 2 + 2 * M * N * 4
+    e2e_skipped = None
+    if e2e_bytes > (8 << 30):
+        e2e_skipped = f"skipped: {e2e_bytes / 2**30:.0f} GiB of pinned host memory over {world} rank(s)"
+        e2e_ms = e2e_serial_ms = float("nan")
+        e2e_ok = None
+        h2d_b = d2h_b = 0
+    else:
+        feat_host = feat.cpu().pin_memory()
+        out_host = [torch.empty(sh.local_rows, N, dtype=torch.float32).pin_memory() for _ in range(2)]
+        feat_dev = torch.empty_like(feat)
+        h2d_b, d2h_b = int(feat_host.numel() * 2) * world, int(out_host[0].numel() * 4) * world
 
-    def e2e_serial_step():
-        feat_dev.copy_(feat_host, non_blocking=True)
-        o = voltrix.spmm(blk, packed, hind, sh.local_rows, sh.local_nnz, feat_dev, out=out)
-        out_host[0].copy_(o, non_blocking=True)
+        def e2e_serial_step():
+            feat_dev.copy_(feat_host, non_blocking=True)
+            o = voltrix.spmm(blk, packed, hind, sh.local_rows, sh.local_nnz, feat_dev, out=out)
+            out_host[0].copy_(o, non_blocking=True)
 
-    n_e2e = max(3, min(args.steps, 10))
+        n_e2e = max(3, min(args.steps, 10))
 
-    def time_e2e(run_steps):
-        run_steps(2)
-        barrier(); s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        run_steps(n_e2e)
-        e.record(); barrier()
-        t2 = torch.tensor([s.elapsed_time(e) / n_e2e], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        return float(t2.item())
+        def time_e2e(run_steps):
+            run_steps(2)
+            barrier(); s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            run_steps(n_e2e)
+            e.record(); barrier()
+            t2 = torch.tensor([s.elapsed_time(e) / n_e2e], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            return float(t2.item())
 
-    def serial_steps(n):
-        for _ in range(n):
-            e2e_serial_step()
+        def serial_steps(n):
+            for _ in range(n):
+                e2e_serial_step()
 
-    e2e_serial_ms = time_e2e(serial_steps)
-    del feat_dev
+        log(f"[rank {rank}] e2e serial leg ...")
+        e2e_serial_ms = time_e2e(serial_steps)
+        log(f"[rank {rank}] e2e serial {e2e_serial_ms:.2f} ms/step; streamed leg ...")
+        del feat_dev
+        pipe = voltrix.HostStreamedSpMM(blk, packed, hind, sh.local_rows, sh.local_nnz, N, dtype=feat.dtype, input_rows=M)
 
-    pipe = voltrix.HostStreamedSpMM(blk, packed, hind, sh.local_rows, sh.local_nnz, N, dtype=feat.dtype, input_rows=M)
+        def streamed_steps(n):
+            pipe.fork()                                         # its streams start after the `s` event on this stream
+            for i in range(n):
+                pipe.submit(feat_host, out_host[i % 2])
+            pipe.join()                                         # this stream (and the `e` event) waits for the last D2H
 
-    def streamed_steps(n):
-        pipe.fork()                                         # its streams start after the `s` event on this stream
-        for i in range(n):
-            pipe.submit(feat_host, out_host[i % 2])
-        pipe.join()                                         # this stream (and the `e` event) waits for the last D2H
-
-    e2e_ms = time_e2e(streamed_steps)
-    e2e_ok = bool(torch.equal(out_host[0], out_host[1]) and torch.equal(out_host[0], out.cpu()))
+        e2e_ms = time_e2e(streamed_steps)
+        e2e_ok = bool(torch.equal(out_host[0], out_host[1]) and torch.equal(out_host[0], out.cpu()))
 
     if rank != 0:
         if world > 1:
@@ -444,11 +465,15 @@ def run_product_arm(args):
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "alg_bytes_per_launch": abytes_local,
                      "alg_bytes_whole_job": abytes,
                      "gather_bytes_per_launch": gather_bytes, "gather_gbs": gather_bytes / (ms * 1e-3) / 1e9,
-                     "note": "B (59.6 MB fp16) is L2-resident: the kernel is bound by the L2->SM gather stream "
-                             "(gather_bytes), not by compulsory HBM bytes -- see DESIGN.md"},
-        "e2e": {"value": flops / e2e_ms / 1e6, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(feat_host.numel() * 2) * world,
-                "d2h_bytes_per_step": int(out_host[0].numel() * 4) * world,
+                     "note": (f"B ({M * N * 2 / 1e6:.1f} MB fp16) is L2-resident: the kernel is bound by the L2->SM gather "
+                              "stream (gather_bytes), not by compulsory HBM bytes -- see DESIGN.md section 4.5")
+                     if M * N * 2 < 100e6 else
+                             (f"B ({M * N * 2 / 1e9:.2f} GB fp16) does not fit the 126 MB L2: the row gather "
+                              "(gather_bytes, minus L2 hits on hub rows) is what HBM actually serves -- DESIGN.md 4.5")},
+        "e2e": {"value": None, "unit": "GFLOP/s", "skipped": e2e_skipped, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        if e2e_skipped else
+               {"value": flops / e2e_ms / 1e6, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "skipped": e2e_skipped,
                 "serial_ms_per_step": e2e_serial_ms, "serial_value": flops / e2e_serial_ms / 1e6,
                 "result_matches_device_run": e2e_ok,
                 "api": "voltrix.HostStreamedSpMM.submit(pinned feat, pinned C): H2D of B, voltrix.spmm, D2H of C "

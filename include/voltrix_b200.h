@@ -108,6 +108,9 @@ typedef struct {
   void *split_ws;              /* model 3 only: bf16 [input_rows][2 * embedding_dim] workspace (else NULL) */
 } vx_plan_t;
 
+/* `stages` (models 0 and 3) = K-steps of 16 gathered rows kept in flight; it selects a compiled variant, each with its
+ * own number of producer warps: 8 (4 warps), 16 (4), 24 (8), 32 (8, the default for any other value), 36 (12), 40 (24),
+ * 42 (14).  36 and 42 are the fast ones on large graphs; model 3 needs 24 or less. */
 int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind, int32_t num_nodes,
             int32_t num_edges, int32_t embedding_dim, const void *input, int32_t input_dtype, float *output,
             int32_t model, int32_t stages, const vx_plan_t *plan, void *stream);

@@ -1,7 +1,11 @@
 #!/bin/bash
-# Multi-GPU bench as the driver launches it.
+# Multi-GPU bench as the driver launches it.  NG=<gpus> WL=<workload> SCALE=<scale> STEPS=<k>
 mkdir -p gpurun_out
-N=${NG:-2}
-nvidia-smi -L > gpurun_out/smi_multi.txt
-echo "== reference arm N=$N"; timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --impl reference --gpus $N --steps 3 --warmup 1 > gpurun_out/bench_ref_n$N.json 2> gpurun_out/bench_ref_n$N.err; echo "rc=$?"; cut -c1-400 gpurun_out/bench_ref_n$N.json
-echo "== product arm N=$N"; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "rc=$?"; cut -c1-1800 gpurun_out/bench_n$N.json; grep -E "rank|Error|error" gpurun_out/bench_n$N.err | tail -8
+N=${NG:-2}; WL=${WL:-reddit}; SCALE=${SCALE:-1.0}; STEPS=${STEPS:-20}
+TAG=${WL}_s${SCALE}_n$N
+if [ "$N" = "1" ]; then
+  timeout ${TMO:-900} python bench.py --gpus 1 --steps $STEPS --warmup 5 --workload $WL --scale $SCALE ${EXTRA} > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+else
+  timeout ${TMO:-900} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps $STEPS --warmup 5 --workload $WL --scale $SCALE ${EXTRA} > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+fi
+echo "rc=$?"; cut -c1-900 gpurun_out/bench_$TAG.json; grep -E "^\[rank|Error|error|Traceback" gpurun_out/bench_$TAG.err | tail -12

@@ -27,8 +27,8 @@ static int spmm_dispatch(const int32_t *blk_offsets, const uint32_t *hspa_packed
     case 16: VX_TC_VARIANT(16, 4);
     case 24: VX_TC_VARIANT(24, 8);
     case 36: VX_TC_VARIANT(36, 12);
-    case 40: VX_TC_VARIANT(40, 16);
-    case 41: VX_TC_VARIANT(40, 24);
+    case 42: VX_TC_VARIANT(42, 14);
+    case 40: VX_TC_VARIANT(40, 24);
     default: VX_TC_VARIANT(32, 8);
   }
 #undef VX_TC_VARIANT

@@ -67,9 +67,9 @@ struct TcGeom {
   static constexpr int kTermB = kFeatTile * 16 * 2;     // one term of one K-step: 16 gathered rows x 128 features x 2 B = 4096
   static constexpr int kKsB = kTermB * TERMS;           // one K-step, all terms
   static constexpr int kKsA = 16 * 16 * 2;              // one K-step: densified 16 x 16 tile = 512
-  // K-steps per stage.  Up to 12 producer warps: one stage = one K-step per warp.  More warps: stages of 8
+  // K-steps per stage.  Up to 16 producer warps: one stage = one K-step per warp.  More warps: stages of 8
   // K-steps owned round-robin by NPW/8 warp groups (more warps in flight without growing the stage).
-  static constexpr int kKsPerStage = NPW > 12 ? 8 : NPW;
+  static constexpr int kKsPerStage = NPW > 16 ? 8 : NPW;
   static constexpr int kGroups = NPW / kKsPerStage;
   static constexpr int kStageB = kKsPerStage * kKsB;
   static constexpr int kStageA = kKsPerStage * kKsA;

@@ -41,8 +41,8 @@ __return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}, {npw}>(
 _CTYPE = {torch.float32: "float", torch.float16: "__half", torch.bfloat16: "__nv_bfloat16"}
 
 # autotune space per input dtype: (model, stages)
-SPACE_HALF = ({"model": 0, "stages": 36, "npw": 12}, {"model": 0, "stages": 40, "npw": 16}, {"model": 0, "stages": 40, "npw": 24},
-              {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
+SPACE_HALF = ({"model": 0, "stages": 36, "npw": 12}, {"model": 0, "stages": 42, "npw": 14}, {"model": 0, "stages": 32, "npw": 16},
+              {"model": 0, "stages": 40, "npw": 24}, {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
 # variants reachable only through the explicit model=/stages= arguments (tests, scripts): prebuilt as well
 EXTRA_HALF = ({"model": 0, "stages": 16, "npw": 4}, {"model": 0, "stages": 32, "npw": 8})
 # fp32: model 3 = tcgen05 on two bf16 terms (hi + lo); models 1 / 2 = exact-fp32 CUDA-core rows
@@ -133,7 +133,7 @@ def spmm_kernel(
     p = plan.launch_args(embedding_dim) if plan is not None else (None, 0, None, 0, None, None, None, None, 0)
     if model is not None:   # explicit variant (tests, benchmarks): a space of one, no timing runs
         stages = int(stages or (24 if int(model) == 3 else 32))
-        npw = int(npw or {8: 4, 16: 4, 36: 12, 40: 16}.get(stages, 8))
+        npw = int(npw or {8: 4, 16: 4, 36: 12, 42: 14, 40: 24}.get(stages, 8))
         space = ({"model": int(model), "stages": stages, "npw": npw},)
         keys = {"ctype": _CTYPE[input.dtype], "fixed": f"{model}/{stages}/{npw}"}
     else:
