@@ -106,6 +106,10 @@ typedef struct {
   int32_t num_sparse_rows;
   int64_t input_rows;          /* rows of `input` (0 = num_nodes); > num_nodes for a row shard of A */
   void *split_ws;              /* model 3 only: bf16 [input_rows][2 * embedding_dim] workspace (else NULL) */
+  /* optional fused epilogue: output = act(row_scale[r] * acc + bias[f]); NULL / 0 = plain SpMM */
+  const float *row_scale;      /* [num_nodes] */
+  const float *bias;           /* [embedding_dim] */
+  int32_t relu;
 } vx_plan_t;
 
 /* `stages` (models 0 and 3) = K-steps of 16 gathered rows kept in flight; it selects a compiled variant, each with its

@@ -239,3 +239,136 @@ def test_host_streamed_pipeline_matches_direct_calls():
     for f, o in zip(feats, outs):
         want = voltrix.spmm(*st, M, E, f.cuda()).cpu()
         assert torch.equal(o, want)
+
+
+def _epilogue_case():
+    """One hub window (K-split -> fix-up pass), ordinary windows (tensor-core epilogue), sparse windows (CSR rows), M % 16 != 0."""
+    rng = np.random.default_rng(9)
+    M = 3001
+    rows, cols = [], []
+    for r in range(M):
+        k = 2500 if r < 16 else (int(rng.integers(20, 120)) if r < 1500 else int(rng.integers(0, 2)))
+        rows.append(np.full(k, r)); cols.append(np.sort(rng.choice(M, size=k, replace=False)))
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    indptr = np.zeros(M + 1, np.int64); np.add.at(indptr, rows + 1, 1)
+    return np.cumsum(indptr).astype(np.int32), cols.astype(np.int32), M
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fused_epilogue_every_model(dtype):
+    """act(row_scale * (A @ B) + bias) applied inside each kernel that writes C equals the unfused result post-processed
+    on the host side -- for every model, including K-split windows (fix-up pass) and CUDA-core sparse rows."""
+    import voltrix
+    indptr, indices, M = _epilogue_case()
+    N = 128
+    rng = np.random.default_rng(1)
+    feat = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32)).cuda().to(dtype)
+    scale = torch.from_numpy(rng.uniform(0.1, 2.0, M).astype(np.float32)).cuda()
+    bias = torch.from_numpy(rng.standard_normal(N).astype(np.float32)).cuda()
+    blk, packed, hind = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
+    plan = packed._vx_plan
+    assert plan.num_fixups >= 1 and plan.num_sparse_rows > 0
+    models = [(1, 32), (2, 32), (3, 24)] if dtype == torch.float32 else [(0, 16), (0, 36), (1, 32), (2, 32)]
+    for model, stages in models:
+        plain = torch.empty(M, N, device="cuda")
+        voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=indices.size, embedding_dim=N, input=feat,
+                            output=plain, model=model, stages=stages)
+        for rs, b, relu in ((scale, None, False), (None, bias, False), (None, None, True), (scale, bias, True)):
+            o = torch.full((M, N), float("nan"), device="cuda")
+            voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=indices.size, embedding_dim=N, input=feat,
+                                output=o, model=model, stages=stages, row_scale=rs, bias=b, relu=relu)
+            want = plain * (rs[:, None] if rs is not None else 1.0) + (b[None, :] if b is not None else 0.0)
+            if relu:
+                want = want.clamp_min(0.0)
+            assert torch.isfinite(o).all()
+            err = (o - want).abs().max().item() / max(want.abs().max().item(), 1e-9)
+            assert err <= 1e-6, (model, stages, rs is not None, b is not None, relu, err)   # one fma of difference
+
+
+def test_gcn_layer_matches_dense_formula():
+    """voltrix.spmm_gcn = relu(D^-1/2 A D^-1/2 X + b) against torch.sparse on the normalised matrix (fp32)."""
+    import voltrix
+    from voltrix.graphs import chung_lu_csr
+    M, N = 30_000, 64
+    indptr, indices = chung_lu_csr(M, avg_degree=20, max_degree=1500, seed=4, device="cuda")
+    E = indices.numel()
+    st = voltrix.csr_preprocess(indptr, indices, M)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.randn(M, N, device="cuda", generator=g)
+    b = torch.randn(N, device="cuda", generator=g)
+    dinv = voltrix.gcn_norm(indptr)
+    got = voltrix.spmm_gcn(*st, M, E, X, dinv, bias=b, relu=True)
+    rows = torch.repeat_interleave(torch.arange(M, device="cuda"), (indptr[1:] - indptr[:-1]).long())
+    vals = dinv[rows] * dinv[indices.long()]
+    A = torch.sparse_csr_tensor(indptr, indices, vals, size=(M, M))
+    want = torch.relu(A @ X + b)
+    assert (got - want).abs().max().item() / want.abs().max().item() <= 5e-5
+
+
+def test_c_abi_plan_with_epilogue():
+    """vx_spmm from libvoltrix_b200.so with a vx_plan_t built by hand (work list + fused epilogue): the struct layout of
+    include/voltrix_b200.h is what the library reads."""
+    import ctypes
+    import os
+    import voltrix
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = ctypes.CDLL(os.path.join(ROOT, "voltrix-spmm_b200", "csrc", "libvoltrix_b200.so"))
+
+    class Plan(ctypes.Structure):
+        _fields_ = [("items", ctypes.c_void_p), ("num_items", ctypes.c_int32), ("fixups", ctypes.c_void_p),
+                    ("num_fixups", ctypes.c_int32), ("scratch", ctypes.c_void_p), ("csr_indptr", ctypes.c_void_p),
+                    ("csr_indices", ctypes.c_void_p), ("sparse_rows", ctypes.c_void_p), ("num_sparse_rows", ctypes.c_int32),
+                    ("input_rows", ctypes.c_int64), ("split_ws", ctypes.c_void_p), ("row_scale", ctypes.c_void_p),
+                    ("bias", ctypes.c_void_p), ("relu", ctypes.c_int32)]
+
+    indptr, indices, M = _epilogue_case()
+    N = 128
+    blk, packed, hind = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
+    p = packed._vx_plan
+    feat = torch.randn(M, N, device="cuda").half()
+    scale = torch.rand(M, device="cuda") + 0.5
+    bias = torch.randn(N, device="cuda")
+    scratch = p.scratch(N)
+    plan = Plan(p.items.data_ptr(), p.num_items, p.fixups.data_ptr(), p.num_fixups, scratch.data_ptr() if scratch is not None else None,
+                p.csr_indptr.data_ptr(), p.csr_indices.data_ptr(), p.sparse_rows.data_ptr(), p.num_sparse_rows, M, None,
+                scale.data_ptr(), bias.data_ptr(), 1)
+    vp, i32 = ctypes.c_void_p, ctypes.c_int32
+    lib.vx_spmm.restype = ctypes.c_int
+    lib.vx_spmm.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, vp, i32, i32, ctypes.POINTER(Plan), vp]
+    out = torch.full((M, N), float("nan"), device="cuda")
+    rc = lib.vx_spmm(blk.data_ptr(), packed.data_ptr(), hind.data_ptr(), M, indices.size, N, feat.data_ptr(), 1,
+                     out.data_ptr(), 0, 36, ctypes.byref(plan), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    want = torch.relu(voltrix.spmm(blk, packed, hind, M, indices.size, feat) * scale[:, None] + bias[None, :])
+    assert torch.isfinite(out).all()
+    assert (out - want).abs().max().item() / want.abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_cuda_graph_capture_and_replay(dtype):
+    """The whole SpMM (tensor-core kernel + fix-up + CUDA-core rows, or split + tensor-core for fp32) is capturable in a CUDA
+    graph once the variant is tuned: nothing on the launch path allocates or synchronises.  Replays see new operand values."""
+    import voltrix
+    indptr, indices, M = _epilogue_case()
+    N = 128
+    st = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
+    E = indices.size
+    feat = torch.randn(M, N, device="cuda").to(dtype)
+    out = torch.empty(M, N, device="cuda")
+    voltrix.spmm(*st, M, E, feat, out=out)          # tune / load outside the capture
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            voltrix.spmm(*st, M, E, feat, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    for seed in (1, 2):
+        feat.copy_(torch.randn(M, N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(seed)).to(dtype))
+        out.fill_(float("nan"))
+        g.replay()
+        torch.cuda.synchronize()
+        want = voltrix.spmm(*st, M, E, feat)
+        assert torch.equal(out, want)

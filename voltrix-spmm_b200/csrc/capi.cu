@@ -36,7 +36,7 @@ static int spmm_dispatch(const int32_t *blk_offsets, const uint32_t *hspa_packed
 
 extern "C" {
 
-int vx_abi_version(void) { return 2; }
+int vx_abi_version(void) { return 3; }
 
 size_t vx_preprocess_workspace_bytes(int64_t num_edges, int32_t num_nodes) {
   return preprocess_workspace_bytes(num_edges, num_nodes);
@@ -120,6 +120,9 @@ int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32
     p.num_sparse_rows = plan->num_sparse_rows;
     p.input_rows = plan->input_rows;
     p.split_ws = plan->split_ws;
+    p.epilogue.row_scale = plan->row_scale;
+    p.epilogue.bias = plan->bias;
+    p.epilogue.relu = plan->relu;
   }
   cudaStream_t s = (cudaStream_t)stream;
   switch (input_dtype) {

@@ -64,6 +64,23 @@ struct __align__(16) WorkItem {
   int32_t slot;
 };
 
+// Optional fused epilogue (no reference counterpart): every kernel that writes C can apply
+//   C[r, f] = act(row_scale[r] * acc[r, f] + bias[f]),  act = ReLU or identity,
+// which covers the GCN layer  relu(D^-1/2 A D^-1/2 X + b)  once X has been pre-scaled by D^-1/2 on its rows
+// (the column scaling of A).  All pointers are optional; default = plain SpMM.
+struct Epilogue {
+  const float *row_scale = nullptr;   // [num_nodes]
+  const float *bias = nullptr;        // [embedding_dim]
+  int32_t relu = 0;
+  __host__ __device__ bool any() const { return row_scale != nullptr || bias != nullptr || relu != 0; }
+  __device__ __forceinline__ float scale_of(int64_t row) const { return row_scale ? __ldg(row_scale + row) : 1.f; }
+  __device__ __forceinline__ float bias_of(int32_t f) const { return bias ? __ldg(bias + f) : 0.f; }
+  __device__ __forceinline__ float apply(float acc, float s, float b) const {
+    const float y = fmaf(acc, s, b);
+    return relu ? fmaxf(y, 0.f) : y;
+  }
+};
+
 // One split window for the fix-up pass.
 struct __align__(16) FixupItem {
   int32_t window;

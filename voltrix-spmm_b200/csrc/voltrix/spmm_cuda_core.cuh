@@ -63,7 +63,7 @@ template <typename T, int LANES>
 __global__ void __launch_bounds__(256)
 vx_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                    const int32_t *__restrict__ row_list, int32_t num_rows, int32_t N,
-                   const T *__restrict__ B, float *__restrict__ C) {
+                   const T *__restrict__ B, float *__restrict__ C, Epilogue epi) {
   constexpr int EPL = Vec16<T>::N;            // elements per lane per load
   constexpr int GROUPS = 32 / LANES;          // non-zeros processed in parallel by one warp
   constexpr int CHUNK = LANES * EPL;          // features covered by one pass
@@ -105,6 +105,11 @@ vx_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
     for (int i = 0; i < EPL; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
   }
   if (grp == 0 && active) {
+    if (epi.any()) {
+      const float sc = epi.scale_of(row);
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) acc[i] = epi.apply(acc[i], sc, epi.bias_of(f0 + i));
+    }
     float4 *dst = reinterpret_cast<float4 *>(C + int64_t(row) * N + f0);
 #pragma unroll
     for (int i = 0; i < EPL / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
@@ -118,7 +123,7 @@ template <typename T, int LANES>
 __global__ void __launch_bounds__(256)
 vx_csr_subwarp_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                            const int32_t *__restrict__ row_list, int32_t num_rows, int32_t N,
-                           const T *__restrict__ B, float *__restrict__ C) {
+                           const T *__restrict__ B, float *__restrict__ C, Epilogue epi) {
   constexpr int EPL = Vec16<T>::N;
   constexpr int CHUNK = LANES * EPL;
   const int32_t item = int32_t((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / LANES);
@@ -142,6 +147,11 @@ vx_csr_subwarp_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__
     Vec16<T>::add(acc, v2); Vec16<T>::add(acc, v3);
   }
   for (; e < end; ++e) Vec16<T>::add(acc, vx_ldg16(Bf + int64_t(__ldg(indices + e)) * N));
+  if (epi.any()) {
+    const float sc = epi.scale_of(row);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) acc[i] = epi.apply(acc[i], sc, epi.bias_of(f0 + i));
+  }
   float4 *dst = reinterpret_cast<float4 *>(C + int64_t(row) * N + f0);
 #pragma unroll
   for (int i = 0; i < EPL / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
@@ -154,7 +164,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 vx_tile_rows_kernel(const int32_t *__restrict__ blk_offsets, const uint32_t *__restrict__ packed,
                     const int32_t *__restrict__ hind, int32_t num_nodes, int32_t N,
-                    const T *__restrict__ B, float *__restrict__ C) {
+                    const T *__restrict__ B, float *__restrict__ C, Epilogue epi) {
   constexpr int EPL = Vec16<T>::N;
   constexpr int CHUNK = 32 * EPL;
   const int lane = threadIdx.x & 31;
@@ -193,6 +203,11 @@ vx_tile_rows_kernel(const int32_t *__restrict__ blk_offsets, const uint32_t *__r
     }
   }
   if (active) {
+    if (epi.any()) {
+      const float sc = epi.scale_of(row);
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) acc[i] = epi.apply(acc[i], sc, epi.bias_of(f0 + i));
+    }
     float4 *dst = reinterpret_cast<float4 *>(C + int64_t(row) * N + f0);
 #pragma unroll
     for (int i = 0; i < EPL / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
@@ -206,7 +221,8 @@ vx_tile_rows_kernel(const int32_t *__restrict__ blk_offsets, const uint32_t *__r
 // has lane groups go to the group-per-row kernel; the choice depends only on (mean_degree, N), never on timing.
 template <typename T>
 inline int launch_csr_rows(const int32_t *indptr, const int32_t *indices, const int32_t *row_list, int32_t num_rows,
-                           int32_t N, const T *B, float *C, cudaStream_t stream, float mean_degree = -1.f) {
+                           int32_t N, const T *B, float *C, cudaStream_t stream, float mean_degree = -1.f,
+                           const Epilogue &epi = Epilogue()) {
   constexpr int EPL = Vec16<T>::N;
   if (num_rows <= 0) return VX_OK;
   if (N <= 0 || N % EPL != 0) return VX_ERR_UNSUPPORTED;
@@ -215,29 +231,30 @@ inline int launch_csr_rows(const int32_t *indptr, const int32_t *indices, const 
   const int lanes = lanes_needed <= 4 ? 4 : lanes_needed <= 8 ? 8 : lanes_needed <= 16 ? 16 : 32;
   if (lanes < 32 && mean_degree >= 0.f && mean_degree < 4.f * float(32 / lanes)) {
     dim3 g(unsigned(ceil_div<int64_t>(int64_t(num_rows) * lanes, 256)), ceil_div(N, lanes * EPL));
-    if (lanes == 4)      vx_csr_subwarp_rows_kernel<T, 4><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
-    else if (lanes == 8) vx_csr_subwarp_rows_kernel<T, 8><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
-    else                 vx_csr_subwarp_rows_kernel<T, 16><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+    if (lanes == 4)      vx_csr_subwarp_rows_kernel<T, 4><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+    else if (lanes == 8) vx_csr_subwarp_rows_kernel<T, 8><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+    else                 vx_csr_subwarp_rows_kernel<T, 16><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
     VX_LAUNCH_CHECK();
     return VX_OK;
   }
   auto grid = [&](int l) { return dim3(ceil_div(num_rows, 8), ceil_div(N, l * EPL)); };
-  if (lanes == 4)       vx_csr_rows_kernel<T, 4><<<grid(4), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
-  else if (lanes == 8)  vx_csr_rows_kernel<T, 8><<<grid(8), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
-  else if (lanes == 16) vx_csr_rows_kernel<T, 16><<<grid(16), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
-  else                  vx_csr_rows_kernel<T, 32><<<grid(32), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C);
+  if (lanes == 4)       vx_csr_rows_kernel<T, 4><<<grid(4), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+  else if (lanes == 8)  vx_csr_rows_kernel<T, 8><<<grid(8), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+  else if (lanes == 16) vx_csr_rows_kernel<T, 16><<<grid(16), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+  else                  vx_csr_rows_kernel<T, 32><<<grid(32), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
   VX_LAUNCH_CHECK();
   return VX_OK;
 }
 
 template <typename T>
 inline int launch_tile_rows(const int32_t *blk_offsets, const uint32_t *packed, const int32_t *hind,
-                            int32_t num_nodes, int32_t N, const T *B, float *C, cudaStream_t stream) {
+                            int32_t num_nodes, int32_t N, const T *B, float *C, cudaStream_t stream,
+                            const Epilogue &epi = Epilogue()) {
   constexpr int EPL = Vec16<T>::N;
   if (num_nodes <= 0) return VX_OK;
   if (N <= 0 || N % EPL != 0) return VX_ERR_UNSUPPORTED;
   dim3 block(256), grid(ceil_div(num_nodes, 8), ceil_div(N, 32 * EPL));
-  vx_tile_rows_kernel<T><<<grid, block, 0, stream>>>(blk_offsets, packed, hind, num_nodes, N, B, C);
+  vx_tile_rows_kernel<T><<<grid, block, 0, stream>>>(blk_offsets, packed, hind, num_nodes, N, B, C, epi);
   VX_LAUNCH_CHECK();
   return VX_OK;
 }

@@ -38,6 +38,7 @@ struct SpmmPlan {
   int64_t input_rows = 0;                // rows of the dense operand (0 = num_nodes, i.e. square A);
                                          // differs for a row shard of A, whose columns span the full matrix
   void *split_ws = nullptr;              // model 3: bf16 [input_rows][2 * embedding_dim] workspace
+  Epilogue epilogue;                     // optional fused row scale / bias / ReLU (default: none)
 };
 
 template <typename T> struct TcSupported { static constexpr bool value = false; };
@@ -59,16 +60,16 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
         if (plan.num_fixups > 0 && plan.scratch == nullptr) return VX_ERR_INVALID_ARG;
         rc = launch_spmm_tc<T, STAGES, NPW>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
                                        hspa_packed, hind, num_nodes, b_rows, embedding_dim, input,
-                                       output, plan.scratch, stream);
+                                       output, plan.scratch, stream, plan.epilogue);
         if (rc != VX_OK) return rc;
         if (plan.num_sparse_rows > 0) {
           if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows) return VX_ERR_INVALID_ARG;
           rc = launch_csr_rows<T>(plan.csr_indptr, plan.csr_indices, plan.sparse_rows, plan.num_sparse_rows,
-                                  embedding_dim, input, output, stream);
+                                  embedding_dim, input, output, stream, -1.f, plan.epilogue);
         }
       } else {
         rc = launch_spmm_tc<T, STAGES, NPW>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind, num_nodes, b_rows,
-                                       embedding_dim, input, output, nullptr, stream);
+                                       embedding_dim, input, output, nullptr, stream, plan.epilogue);
       }
       return rc;
     } else {
@@ -77,9 +78,10 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
   } else if (model == 1) {
     if (!plan.csr_indptr || !plan.csr_indices) return VX_ERR_INVALID_ARG;
     return launch_csr_rows<T>(plan.csr_indptr, plan.csr_indices, nullptr, num_nodes, embedding_dim, input, output,
-                              stream, float(num_edges) / float(num_nodes));
+                              stream, float(num_edges) / float(num_nodes), plan.epilogue);
   } else if (model == 2) {
-    return launch_tile_rows<T>(blks_offsets, hspa_packed, hind, num_nodes, embedding_dim, input, output, stream);
+    return launch_tile_rows<T>(blks_offsets, hspa_packed, hind, num_nodes, embedding_dim, input, output, stream,
+                               plan.epilogue);
   } else if (model == 3) {
     if constexpr (std::is_same<T, float>::value && tc_smem_bytes<STAGES, NPW, 2>() <= 227 * 1024) {
       if (plan.split_ws == nullptr) return VX_ERR_INVALID_ARG;
@@ -91,17 +93,18 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
       if (plan.items != nullptr) {
         rc = launch_spmm_tc<__nv_bfloat16, STAGES, NPW, 2>(plan.items, plan.num_items, plan.fixups, plan.num_fixups,
                                                            blks_offsets, hspa_packed, hind, num_nodes, b_rows,
-                                                           embedding_dim, terms, output, plan.scratch, stream);
+                                                           embedding_dim, terms, output, plan.scratch, stream,
+                                                           plan.epilogue);
         if (rc != VX_OK) return rc;
         if (plan.num_sparse_rows > 0) {   // sparse windows: exact fp32 rows from the original operand
           if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows) return VX_ERR_INVALID_ARG;
           rc = launch_csr_rows<T>(plan.csr_indptr, plan.csr_indices, plan.sparse_rows, plan.num_sparse_rows,
-                                  embedding_dim, input, output, stream);
+                                  embedding_dim, input, output, stream, -1.f, plan.epilogue);
         }
       } else {
         rc = launch_spmm_tc<__nv_bfloat16, STAGES, NPW, 2>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind,
                                                            num_nodes, b_rows, embedding_dim, terms, output, nullptr,
-                                                           stream);
+                                                           stream, plan.epilogue);
       }
       return rc;
     } else {

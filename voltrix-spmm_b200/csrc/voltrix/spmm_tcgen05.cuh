@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(TcGeom<NPW, TERMS>::kThreads, 1)
 vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__restrict__ items, int32_t num_items,
                   int32_t n_feat_tiles, const int32_t *__restrict__ blk_offsets, const uint4 *__restrict__ packed,
                   const int4 *__restrict__ hind4, int32_t num_nodes, int32_t N, float *__restrict__ C,
-                  float *__restrict__ scratch, int32_t term_stride) {
+                  float *__restrict__ scratch, int32_t term_stride, Epilogue epi) {
   using G = TcGeom<NPW, TERMS>;
   static_assert(NPW % G::kKsPerStage == 0, "producer warps must form whole groups");
   static_assert(KSTEPS % G::kKsPerStage == 0 && KSTEPS / G::kKsPerStage > G::kGroups,
@@ -373,6 +373,13 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
         if (it.slot < 0) {
           dst = C + int64_t(it.window) * BLK_H * N + f;
           nrows = min(BLK_H, num_nodes - it.window * BLK_H);   // partial tail window: rows >= M do not exist
+          if (epi.any()) {   // fused epilogue; K-split partial tiles (slot >= 0) get it in the fix-up pass instead
+            const float bf = epi.bias_of(f);
+#pragma unroll
+            for (int r = 0; r < BLK_H; ++r)
+              if (r < nrows)
+                v[r] = __float_as_uint(epi.apply(__uint_as_float(v[r]), epi.scale_of(int64_t(it.window) * BLK_H + r), bf));
+          }
         } else {
           dst = scratch + int64_t(it.slot) * BLK_H * N + f;
         }
@@ -391,7 +398,7 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
 // Sums the partial tiles of K-split windows in slot order (fixed order => deterministic).
 __global__ void vx_fixup_kernel(const FixupItem *__restrict__ fixups, int32_t num_fixups,
                                 const float *__restrict__ scratch, int32_t num_nodes, int32_t N,
-                                float *__restrict__ C) {
+                                float *__restrict__ C, Epilogue epi) {
   const int32_t i = blockIdx.x;
   if (i >= num_fixups) return;
   const FixupItem fx = fixups[i];
@@ -400,6 +407,7 @@ __global__ void vx_fixup_kernel(const FixupItem *__restrict__ fixups, int32_t nu
   for (int32_t e = threadIdx.x; e < elems; e += blockDim.x) {
     float s = 0.f;
     for (int32_t k = 0; k < fx.slot_count; ++k) s += scratch[int64_t(fx.slot_begin + k) * BLK_H * N + e];
+    if (epi.any()) s = epi.apply(s, epi.scale_of(int64_t(fx.window) * BLK_H + e / N), epi.bias_of(e % N));
     C[int64_t(fx.window) * BLK_H * N + e] = s;
   }
 }
@@ -460,7 +468,8 @@ template <typename T, int STAGES, int NPW, int TERMS = 1>
 inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupItem *fixups, int32_t num_fixups,
                           const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind,
                           int32_t num_nodes, int64_t b_rows,
-                          int32_t N, const T *B, float *C, float *scratch, cudaStream_t stream) {
+                          int32_t N, const T *B, float *C, float *scratch, cudaStream_t stream,
+                          const Epilogue &epi = Epilogue()) {
   if (num_items <= 0) return VX_OK;
   if (N % 8 != 0 || (reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(hind) & 15) ||
       (reinterpret_cast<uintptr_t>(hspa_packed) & 15))
@@ -480,10 +489,10 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
   const int grid = int(total_units < device_sm_count() ? total_units : device_sm_count());
   kern<<<grid, G::kThreads, smem, stream>>>(tmap, items, num_items, n_feat_tiles, blk_offsets,
                                                  reinterpret_cast<const uint4 *>(hspa_packed),
-                                                 reinterpret_cast<const int4 *>(hind), num_nodes, N, C, scratch, N);
+                                                 reinterpret_cast<const int4 *>(hind), num_nodes, N, C, scratch, N, epi);
   VX_LAUNCH_CHECK();
   if (num_fixups > 0) {
-    vx_fixup_kernel<<<num_fixups, 256, 0, stream>>>(fixups, num_fixups, scratch, num_nodes, N, C);
+    vx_fixup_kernel<<<num_fixups, 256, 0, stream>>>(fixups, num_fixups, scratch, num_nodes, N, C, epi);
     VX_LAUNCH_CHECK();
   }
   return VX_OK;

@@ -33,6 +33,9 @@ plan.sparse_rows = sparse_rows;
 plan.num_sparse_rows = num_sparse_rows;
 plan.input_rows = input_rows;
 plan.split_ws = split_ws;
+plan.epilogue.row_scale = row_scale;
+plan.epilogue.bias = bias;
+plan.epilogue.relu = relu;
 __return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}, {npw}>(
     blk_offsets, hspa_packed, hind,
     num_nodes, num_edges, embedding_dim, input, output, {model}, plan, stream);
@@ -70,6 +73,9 @@ def arg_defs_for(dtype):
         ("num_sparse_rows", int),
         ("input_rows", int),
         ("split_ws", torch.bfloat16),
+        ("row_scale", torch.float32),
+        ("bias", torch.float32),
+        ("relu", int),
         ("stream", torch.cuda.Stream),
     )
 
@@ -120,13 +126,24 @@ def spmm_kernel(
     model=None,
     stages=None,
     npw=None,
+    row_scale=None,
+    bias=None,
+    relu=False,
 ):
+    """Extensions beyond the reference's signature: ``plan`` / ``model`` / ``stages`` / ``npw`` (explicit variant), and the
+    fused epilogue ``output = act(row_scale[:, None] * (A @ input) + bias[None, :])`` with fp32 ``row_scale [num_nodes]``,
+    fp32 ``bias [embedding_dim]`` and ``act`` = ReLU when ``relu`` (all optional, applied in the kernel that writes C)."""
     assert blk_offsets.is_cuda and blk_offsets.dtype == torch.int32
     assert hspa_packed.is_cuda and hspa_packed.dtype == torch.uint32
     assert hind.is_cuda and hind.dtype == torch.int32
     assert input.is_cuda and input.dtype in _CTYPE and input.is_contiguous()
     assert output.is_cuda and output.dtype == torch.float and output.is_contiguous()
     assert input.shape[-1] == embedding_dim and output.shape[-1] == embedding_dim
+    if row_scale is not None:
+        assert row_scale.is_cuda and row_scale.dtype == torch.float32 and row_scale.is_contiguous()
+        assert row_scale.numel() == num_nodes
+    if bias is not None:
+        assert bias.is_cuda and bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == embedding_dim
 
     if plan is None:
         plan = getattr(hspa_packed, "_vx_plan", None)
@@ -150,7 +167,7 @@ def spmm_kernel(
             (winner is None or winner.get("model") == 3):
         split_ws = _split_workspace(ws_owner, int(input.shape[0]), embedding_dim, input.device)
     args = (blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, input, output, *p,
-            int(input.shape[0]), split_ws, current_stream())
+            int(input.shape[0]), split_ws, row_scale, bias, int(bool(relu)), current_stream())
 
     runtime = jit_tuner.compile_and_tune(
         name="spmm_kernel",

@@ -4,4 +4,6 @@ from .spmm import (
     spmm,
     SpmmPlan,
     HostStreamedSpMM,
+    gcn_norm,
+    spmm_gcn,
 )

@@ -176,7 +176,12 @@ def spmm(
     num_edges: int,
     feat: torch.Tensor,
     out: Optional[torch.Tensor] = None,
+    row_scale: Optional[torch.Tensor] = None,
+    bias: Optional[torch.Tensor] = None,
+    relu: bool = False,
 ):
+    """Reference signature (voltrix/spmm/spmm.py:92-101) plus keyword extensions: ``out`` (caller-owned result) and the
+    fused epilogue ``act(row_scale[:, None] * (A @ feat) + bias)`` (see ``spmm_kernel``)."""
     num_feats = feat.shape[1]
     output = out if out is not None else torch.empty((num_nodes, num_feats), dtype=torch.float32, device=feat.device)
 
@@ -189,9 +194,27 @@ def spmm(
         embedding_dim=num_feats,
         input=feat,
         output=output,
+        row_scale=row_scale,
+        bias=bias,
+        relu=relu,
     )
 
     return output
+
+
+def gcn_norm(indptr: torch.Tensor) -> torch.Tensor:
+    """``D^-1/2`` of a binary adjacency matrix given its CSR row pointer (isolated rows get 0), fp32, on indptr's device."""
+    deg = (indptr[1:] - indptr[:-1]).to(torch.float32)
+    return torch.where(deg > 0, deg.rsqrt(), torch.zeros_like(deg))
+
+
+def spmm_gcn(blk_offsets, hspa_packed, hind, num_nodes: int, num_edges: int, feat: torch.Tensor, dinv: torch.Tensor,
+             bias: Optional[torch.Tensor] = None, relu: bool = False, out: Optional[torch.Tensor] = None):
+    """One GCN propagation ``act(D^-1/2 A D^-1/2 X + b)`` for a square binary A: the column scaling is folded into X
+    (one elementwise pass over the dense operand), the row scaling, bias and activation run in the SpMM epilogue.
+    The tile format has no value array (reference bmat_kernels.cuh:102): this is how normalised adjacency is served."""
+    scaled = (feat.float() * dinv[:, None]).to(feat.dtype)
+    return spmm(blk_offsets, hspa_packed, hind, num_nodes, num_edges, scaled, out=out, row_scale=dinv, bias=bias, relu=relu)
 
 
 class HostStreamedSpMM:
