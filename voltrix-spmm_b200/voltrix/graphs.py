@@ -189,3 +189,30 @@ def suite_graph(name: str, seed: int = 0, device="cuda"):
             return chung_lu_csr(M, avg_degree=avg, max_degree=max(avg * 2, min(M / 8, avg * 40)), seed=seed,
                                 device=device, target_nnz=nnz)
     raise KeyError(name)
+
+
+def planted_partition_csr(M: int, community: int, p_in: float, p_out: float, seed: int = 0, device="cpu",
+                          shuffle: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Symmetric stochastic block model with equal communities of ``community`` nodes (edge probability ``p_in`` inside,
+    ``p_out`` across), node labels shuffled when ``shuffle`` -- the structure real GNN graphs have and the Chung-Lu
+    stand-ins lack; used to exercise voltrix.reorder."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    C = (M + community - 1) // community
+    col_bits = max(1, int(M - 1).bit_length())
+    parts = []
+    # inside: per community a dense Bernoulli block (upper triangle), across: a global sparse sample
+    n_in = int(C * community * (community - 1) / 2 * p_in * 1.05) + 16
+    c = torch.randint(0, C, (n_in,), generator=g, device=dev)
+    u = c * community + torch.randint(0, community, (n_in,), generator=g, device=dev)
+    v = c * community + torch.randint(0, community, (n_in,), generator=g, device=dev)
+    parts.append((u, v))
+    n_out = int(M * (M - community) / 2 * p_out) + 16
+    parts.append((torch.randint(0, M, (n_out,), generator=g, device=dev), torch.randint(0, M, (n_out,), generator=g, device=dev)))
+    u = torch.cat([p[0] for p in parts]); v = torch.cat([p[1] for p in parts])
+    keep = (u != v) & (u < M) & (v < M)
+    u, v = u[keep], v[keep]
+    if shuffle:
+        label = torch.randperm(M, generator=g, device=dev)
+        u, v = label[u], label[v]
+    return _csr_from_keys(torch.cat([(u << col_bits) | v, (v << col_bits) | u]), M, col_bits)

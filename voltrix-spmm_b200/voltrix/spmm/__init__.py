@@ -5,5 +5,7 @@ from .spmm import (
     SpmmPlan,
     HostStreamedSpMM,
     gcn_norm,
+    save_preprocessed,
+    load_preprocessed,
     spmm_gcn,
 )

@@ -280,3 +280,58 @@ class HostStreamedSpMM:
     def wait(self):
         for s in (self.s_in, self.s_run, self.s_out):
             s.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# On-disk format of a preprocessed matrix: preprocessing + scheduling are paid once
+# per graph, the autotuner's winners already persist in <cache>/tuned.json; this closes the loop across processes.
+# ------------------------------------------------------------------------------------------------------------
+FORMAT_VERSION = 1
+_PLAN_TENSORS = ("items", "fixups", "sparse_rows", "csr_indptr", "csr_indices", "block_partition")
+_PLAN_SCALARS = ("num_nodes", "num_edges", "total_blocks", "unique_nnz", "cap", "sparse_ratio", "num_items", "num_slots",
+                 "num_fixups", "num_sparse_rows")
+
+
+def save_preprocessed(path: str, blk_offsets: torch.Tensor, hspa_packed: torch.Tensor, hind: torch.Tensor,
+                      hash_tag: Optional[str] = None) -> None:
+    """Write the reference-format triple and the work list / CSR state hung off ``hspa_packed`` to ``path`` (torch.save of
+    CPU tensors).  ``hash_tag`` (default: the one set on ``hspa_packed``, if any) is stored so that a reloaded matrix maps
+    to the same autotune key."""
+    plan = getattr(hspa_packed, "_vx_plan", None)
+    blob = {
+        "format": "voltrix-b200-tiles", "version": FORMAT_VERSION, "BLK_H": BLK_H, "BLK_W": BLK_W,
+        "blk_offsets": blk_offsets.cpu(), "hspa_packed": hspa_packed.cpu().view(torch.int32), "hind": hind.cpu(),
+        "hash_tag": hash_tag if hash_tag is not None else getattr(hspa_packed, "hash_tag", None),
+        "plan": None,
+    }
+    if plan is not None:
+        blob["plan"] = {"scalars": {k: getattr(plan, k) for k in _PLAN_SCALARS},
+                        "tensors": {k: (getattr(plan, k).cpu() if getattr(plan, k) is not None else None)
+                                    for k in _PLAN_TENSORS}}
+    torch.save(blob, path)
+
+
+def load_preprocessed(path: str, device=None):
+    """Inverse of ``save_preprocessed``: returns ``(blk_offsets, hspa_packed, hind)`` on ``device`` (default: the current
+    CUDA device) with the plan and ``hash_tag`` re-attached, ready for ``spmm``."""
+    blob = torch.load(path, map_location="cpu", weights_only=True)
+    if blob.get("format") != "voltrix-b200-tiles" or blob.get("version") != FORMAT_VERSION:
+        raise ValueError(f"{path}: not a voltrix-b200 tile file of version {FORMAT_VERSION}")
+    if blob["BLK_H"] != BLK_H or blob["BLK_W"] != BLK_W:
+        raise ValueError(f"{path}: tile geometry {blob['BLK_H']}x{blob['BLK_W']} does not match {BLK_H}x{BLK_W}")
+    if device is None:
+        require_cuda()
+        device = torch.device("cuda", torch.cuda.current_device())
+    blk_offsets = blob["blk_offsets"].to(device)
+    hspa_packed = blob["hspa_packed"].view(torch.uint32).to(device)
+    hind = blob["hind"].to(device)
+    if blob["plan"] is not None:
+        plan = SpmmPlan()
+        for k, v in blob["plan"]["scalars"].items():
+            setattr(plan, k, v)
+        for k, v in blob["plan"]["tensors"].items():
+            setattr(plan, k, v.to(device) if v is not None else None)
+        hspa_packed._vx_plan = plan
+    if blob["hash_tag"] is not None:
+        hspa_packed.hash_tag = blob["hash_tag"]
+    return blk_offsets, hspa_packed, hind
