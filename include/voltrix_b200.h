@@ -119,6 +119,13 @@ int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32
             int32_t num_edges, int32_t embedding_dim, const void *input, int32_t input_dtype, float *output,
             int32_t model, int32_t stages, const vx_plan_t *plan, void *stream);
 
+/* ---- general CSR x dense with fp32 values (no reference counterpart: its format is binary, bmat_kernels.cuh:102) ----
+ * output[r, :] = act(row_scale[r] * sum_e values[e] * input[indices[e], :] + bias), CUDA-core rows, fp32 accumulate.
+ * Duplicate (row, col) entries add up.  row_scale / bias may be NULL. */
+int vx_spmm_csr_weighted(const int32_t *indptr, const int32_t *indices, const float *values, int32_t num_rows,
+                         int64_t num_edges, int32_t embedding_dim, const void *input, int32_t input_dtype, float *output,
+                         const float *row_scale, const float *bias, int32_t relu, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

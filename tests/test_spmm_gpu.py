@@ -372,3 +372,26 @@ def test_cuda_graph_capture_and_replay(dtype):
         torch.cuda.synchronize()
         want = voltrix.spmm(*st, M, E, feat)
         assert torch.equal(out, want)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("density,N", [(3.0 / 4000, 32), (0.02, 128), (0.02, 512)])
+def test_weighted_csr_spmm(dtype, density, N):
+    """voltrix.spmm_weighted (general CSR values, CUDA-core rows, both the warp-per-row and the group-per-row kernel)
+    against scipy on the same rounded operand; with and without the fused epilogue."""
+    import scipy.sparse as sp
+    import voltrix
+    M = 4000
+    A = sp.random(M, M, density=density, format="csr", random_state=np.random.default_rng(3), dtype=np.float32)
+    A.data = np.random.default_rng(4).standard_normal(A.nnz).astype(np.float32)
+    feat = torch.from_numpy(np.random.default_rng(5).standard_normal((M, N)).astype(np.float32)).cuda().to(dtype)
+    ip, ix, vals = (torch.from_numpy(A.indptr.astype(np.int32)), torch.from_numpy(A.indices.astype(np.int32)),
+                    torch.from_numpy(A.data))
+    want = A @ feat.float().cpu().numpy()
+    got = voltrix.spmm_weighted(ip.cuda(), ix.cuda(), vals.cuda(), feat).cpu().numpy()
+    assert _scaled_err(got, want) <= 2e-5
+    scale = torch.rand(M, device="cuda") + 0.5
+    bias = torch.randn(N, device="cuda")
+    got2 = voltrix.spmm_weighted(ip, ix, vals, feat, row_scale=scale, bias=bias, relu=True).cpu().numpy()
+    want2 = np.maximum(want * scale.cpu().numpy()[:, None] + bias.cpu().numpy()[None, :], 0.0)
+    assert _scaled_err(got2, want2) <= 2e-5

@@ -34,9 +34,17 @@ static int spmm_dispatch(const int32_t *blk_offsets, const uint32_t *hspa_packed
 #undef VX_TC_VARIANT
 }
 
+template <typename T>
+static int csr_weighted_dispatch(const int32_t *indptr, const int32_t *indices, const float *values, int32_t num_rows,
+                                 int64_t num_edges, int32_t embedding_dim, const void *input, float *output,
+                                 const Epilogue &epi, cudaStream_t stream) {
+  return launch_csr_rows_weighted<T>(indptr, indices, values, num_rows, num_edges, embedding_dim,
+                                     static_cast<const T *>(input), output, stream, epi);
+}
+
 extern "C" {
 
-int vx_abi_version(void) { return 3; }
+int vx_abi_version(void) { return 4; }
 
 size_t vx_preprocess_workspace_bytes(int64_t num_edges, int32_t num_nodes) {
   return preprocess_workspace_bytes(num_edges, num_nodes);
@@ -135,6 +143,22 @@ int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32
     case VX_DTYPE_BF16:
       return spmm_dispatch<__nv_bfloat16>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, input,
                                           output, model, stages, p, s);
+  }
+  return VX_ERR_INVALID_ARG;
+}
+
+int vx_spmm_csr_weighted(const int32_t *indptr, const int32_t *indices, const float *values, int32_t num_rows,
+                         int64_t num_edges, int32_t embedding_dim, const void *input, int32_t input_dtype, float *output,
+                         const float *row_scale, const float *bias, int32_t relu, void *stream) {
+  Epilogue epi;
+  epi.row_scale = row_scale;
+  epi.bias = bias;
+  epi.relu = relu;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (input_dtype) {
+    case VX_DTYPE_F32: return csr_weighted_dispatch<float>(indptr, indices, values, num_rows, num_edges, embedding_dim, input, output, epi, s);
+    case VX_DTYPE_F16: return csr_weighted_dispatch<__half>(indptr, indices, values, num_rows, num_edges, embedding_dim, input, output, epi, s);
+    case VX_DTYPE_BF16: return csr_weighted_dispatch<__nv_bfloat16>(indptr, indices, values, num_rows, num_edges, embedding_dim, input, output, epi, s);
   }
   return VX_ERR_INVALID_ARG;
 }

@@ -25,6 +25,10 @@ namespace voltrix {
 template <typename T> struct Vec16;  // 16 bytes of T, unpacked to fp32
 template <> struct Vec16<float> {
   static constexpr int N = 4;
+  __device__ static void fma(float (&acc)[4], const uint4 &v, float w) {
+    acc[0] = fmaf(w, __uint_as_float(v.x), acc[0]); acc[1] = fmaf(w, __uint_as_float(v.y), acc[1]);
+    acc[2] = fmaf(w, __uint_as_float(v.z), acc[2]); acc[3] = fmaf(w, __uint_as_float(v.w), acc[3]);
+  }
   __device__ static void add(float (&acc)[4], const uint4 &v) {
     acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y);
     acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
@@ -32,6 +36,14 @@ template <> struct Vec16<float> {
 };
 template <> struct Vec16<__half> {
   static constexpr int N = 8;
+  __device__ static void fma(float (&acc)[8], const uint4 &v, float w) {
+    const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(h[i]);
+      acc[2 * i] = fmaf(w, f.x, acc[2 * i]); acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
+    }
+  }
   __device__ static void add(float (&acc)[8], const uint4 &v) {
     const __half2 *h = reinterpret_cast<const __half2 *>(&v);
 #pragma unroll
@@ -43,6 +55,14 @@ template <> struct Vec16<__half> {
 };
 template <> struct Vec16<__nv_bfloat16> {
   static constexpr int N = 8;
+  __device__ static void fma(float (&acc)[8], const uint4 &v, float w) {
+    const uint32_t *x = reinterpret_cast<const uint32_t *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] = fmaf(w, __uint_as_float(x[i] << 16), acc[2 * i]);
+      acc[2 * i + 1] = fmaf(w, __uint_as_float(x[i] & 0xffff0000u), acc[2 * i + 1]);
+    }
+  }
   __device__ static void add(float (&acc)[8], const uint4 &v) {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(&v);
 #pragma unroll
@@ -59,11 +79,13 @@ __device__ __forceinline__ uint4 vx_ldg16(const void *p) {
 
 // rows: either all rows [0, num_rows) (row_list == nullptr) or the rows named by
 // row_list[0..num_rows).  grid.x * warps_per_block >= num_rows, grid.y = feature chunks.
-template <typename T, int LANES>
+// WEIGHTED: `vals[e]` multiplies the gathered row of non-zero e (general CSR values).  The
+// binary instantiation is the product path of the tile format; the weighted one serves voltrix.spmm_weighted.
+template <typename T, int LANES, bool WEIGHTED = false>
 __global__ void __launch_bounds__(256)
 vx_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                    const int32_t *__restrict__ row_list, int32_t num_rows, int32_t N,
-                   const T *__restrict__ B, float *__restrict__ C, Epilogue epi) {
+                   const T *__restrict__ B, float *__restrict__ C, Epilogue epi, const float *__restrict__ vals = nullptr) {
   constexpr int EPL = Vec16<T>::N;            // elements per lane per load
   constexpr int GROUPS = 32 / LANES;          // non-zeros processed in parallel by one warp
   constexpr int CHUNK = LANES * EPL;          // features covered by one pass
@@ -90,13 +112,21 @@ vx_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
     if (active) {
       uint4 v0 = vx_ldg16(Bf + int64_t(c0) * N), v1 = vx_ldg16(Bf + int64_t(c1) * N);
       uint4 v2 = vx_ldg16(Bf + int64_t(c2) * N), v3 = vx_ldg16(Bf + int64_t(c3) * N);
-      Vec16<T>::add(acc, v0); Vec16<T>::add(acc, v1);
-      Vec16<T>::add(acc, v2); Vec16<T>::add(acc, v3);
+      if constexpr (WEIGHTED) {
+        Vec16<T>::fma(acc, v0, __ldg(vals + e)); Vec16<T>::fma(acc, v1, __ldg(vals + e + GROUPS));
+        Vec16<T>::fma(acc, v2, __ldg(vals + e + 2 * GROUPS)); Vec16<T>::fma(acc, v3, __ldg(vals + e + 3 * GROUPS));
+      } else {
+        Vec16<T>::add(acc, v0); Vec16<T>::add(acc, v1);
+        Vec16<T>::add(acc, v2); Vec16<T>::add(acc, v3);
+      }
     }
   }
   for (; e < end; e += GROUPS) {
     int32_t c0 = __ldg(indices + e);
-    if (active) Vec16<T>::add(acc, vx_ldg16(Bf + int64_t(c0) * N));
+    if (active) {
+      if constexpr (WEIGHTED) Vec16<T>::fma(acc, vx_ldg16(Bf + int64_t(c0) * N), __ldg(vals + e));
+      else Vec16<T>::add(acc, vx_ldg16(Bf + int64_t(c0) * N));
+    }
   }
   // fixed-order tree reduction over the lane groups (deterministic)
 #pragma unroll
@@ -119,11 +149,12 @@ vx_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
 // Low-degree variant: one lane GROUP (LANES threads) per row, 32 / LANES rows per warp, no cross-group reduction.
 // With a mean degree of 2-10 (Yeast, DD, com-amazon ... in the C3 suite) a whole warp per row leaves most lane groups
 // without a non-zero; here every group walks its own row, 4 gathers deep.
-template <typename T, int LANES>
+template <typename T, int LANES, bool WEIGHTED = false>
 __global__ void __launch_bounds__(256)
 vx_csr_subwarp_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                            const int32_t *__restrict__ row_list, int32_t num_rows, int32_t N,
-                           const T *__restrict__ B, float *__restrict__ C, Epilogue epi) {
+                           const T *__restrict__ B, float *__restrict__ C, Epilogue epi,
+                           const float *__restrict__ vals = nullptr) {
   constexpr int EPL = Vec16<T>::N;
   constexpr int CHUNK = LANES * EPL;
   const int32_t item = int32_t((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / LANES);
@@ -143,10 +174,19 @@ vx_csr_subwarp_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__
                   c3 = __ldg(indices + e + 3);
     const uint4 v0 = vx_ldg16(Bf + int64_t(c0) * N), v1 = vx_ldg16(Bf + int64_t(c1) * N);
     const uint4 v2 = vx_ldg16(Bf + int64_t(c2) * N), v3 = vx_ldg16(Bf + int64_t(c3) * N);
-    Vec16<T>::add(acc, v0); Vec16<T>::add(acc, v1);
-    Vec16<T>::add(acc, v2); Vec16<T>::add(acc, v3);
+    if constexpr (WEIGHTED) {
+      Vec16<T>::fma(acc, v0, __ldg(vals + e)); Vec16<T>::fma(acc, v1, __ldg(vals + e + 1));
+      Vec16<T>::fma(acc, v2, __ldg(vals + e + 2)); Vec16<T>::fma(acc, v3, __ldg(vals + e + 3));
+    } else {
+      Vec16<T>::add(acc, v0); Vec16<T>::add(acc, v1);
+      Vec16<T>::add(acc, v2); Vec16<T>::add(acc, v3);
+    }
   }
-  for (; e < end; ++e) Vec16<T>::add(acc, vx_ldg16(Bf + int64_t(__ldg(indices + e)) * N));
+  for (; e < end; ++e) {
+    const uint4 v = vx_ldg16(Bf + int64_t(__ldg(indices + e)) * N);
+    if constexpr (WEIGHTED) Vec16<T>::fma(acc, v, __ldg(vals + e));
+    else Vec16<T>::add(acc, v);
+  }
   if (epi.any()) {
     const float sc = epi.scale_of(row);
 #pragma unroll
@@ -242,6 +282,36 @@ inline int launch_csr_rows(const int32_t *indptr, const int32_t *indices, const 
   else if (lanes == 8)  vx_csr_rows_kernel<T, 8><<<grid(8), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
   else if (lanes == 16) vx_csr_rows_kernel<T, 16><<<grid(16), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
   else                  vx_csr_rows_kernel<T, 32><<<grid(32), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+  VX_LAUNCH_CHECK();
+  return VX_OK;
+}
+
+// General CSR SpMM with fp32 values (duplicated (row, col) entries add up, as in any CSR product).
+template <typename T>
+inline int launch_csr_rows_weighted(const int32_t *indptr, const int32_t *indices, const float *vals, int32_t num_rows,
+                                    int64_t num_edges, int32_t N, const T *B, float *C, cudaStream_t stream,
+                                    const Epilogue &epi = Epilogue()) {
+  constexpr int EPL = Vec16<T>::N;
+  if (num_rows <= 0) return VX_OK;
+  if (vals == nullptr) return VX_ERR_INVALID_ARG;
+  if (N <= 0 || N % EPL != 0) return VX_ERR_UNSUPPORTED;
+  const int lanes_needed = N / EPL;
+  const int lanes = lanes_needed <= 4 ? 4 : lanes_needed <= 8 ? 8 : lanes_needed <= 16 ? 16 : 32;
+  const float mean_degree = float(num_edges) / float(num_rows);
+  dim3 block(256);
+  if (lanes < 32 && mean_degree < 4.f * float(32 / lanes)) {
+    dim3 g(unsigned(ceil_div<int64_t>(int64_t(num_rows) * lanes, 256)), ceil_div(N, lanes * EPL));
+    if (lanes == 4)      vx_csr_subwarp_rows_kernel<T, 4, true><<<g, block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+    else if (lanes == 8) vx_csr_subwarp_rows_kernel<T, 8, true><<<g, block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+    else                 vx_csr_subwarp_rows_kernel<T, 16, true><<<g, block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+    VX_LAUNCH_CHECK();
+    return VX_OK;
+  }
+  auto grid = [&](int l) { return dim3(ceil_div(num_rows, 8), ceil_div(N, l * EPL)); };
+  if (lanes == 4)       vx_csr_rows_kernel<T, 4, true><<<grid(4), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+  else if (lanes == 8)  vx_csr_rows_kernel<T, 8, true><<<grid(8), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+  else if (lanes == 16) vx_csr_rows_kernel<T, 16, true><<<grid(16), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+  else                  vx_csr_rows_kernel<T, 32, true><<<grid(32), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
   VX_LAUNCH_CHECK();
   return VX_OK;
 }

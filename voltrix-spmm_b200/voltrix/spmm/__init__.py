@@ -5,6 +5,7 @@ from .spmm import (
     SpmmPlan,
     HostStreamedSpMM,
     gcn_norm,
+    spmm_weighted,
     save_preprocessed,
     load_preprocessed,
     spmm_gcn,

@@ -28,6 +28,7 @@ from ..jit_kernels import (
     schedule_build_kernel,
     schedule_sizes,
     schedule_sort_kernel,
+    spmm_csr_weighted_kernel,
     spmm_kernel,
 )
 from ..jit_kernels._common import alloc_workspace, require_cuda
@@ -199,6 +200,24 @@ def spmm(
         relu=relu,
     )
 
+    return output
+
+
+def spmm_weighted(indptr: torch.Tensor, indices: torch.Tensor, values: torch.Tensor, feat: torch.Tensor,
+                  out: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
+                  bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """``act(row_scale * (A @ feat) + bias)`` for a CSR matrix WITH values (fp32 ``values[nnz]``), straight from CSR, no
+    preprocessing: the vectorised CUDA-core row kernels with a multiply per gathered row.  ``feat`` fp32 / fp16 / bf16,
+    fp32 accumulation and output.  Duplicate (row, col) entries add up (the binary tile path counts them once)."""
+    require_cuda()
+    dev = feat.device
+    indptr = indptr.to(dev, non_blocking=True).contiguous()
+    indices = indices.to(dev, non_blocking=True).contiguous()
+    values = values.to(dev, torch.float32, non_blocking=True).contiguous()
+    num_rows, num_feats = indptr.numel() - 1, feat.shape[1]
+    output = out if out is not None else torch.empty((num_rows, num_feats), dtype=torch.float32, device=dev)
+    spmm_csr_weighted_kernel(indptr, indices, values, num_rows, num_feats, feat, output, row_scale=row_scale, bias=bias,
+                             relu=relu)
     return output
 
 
