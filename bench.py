@@ -158,6 +158,25 @@ def cpu_baseline(indptr_h: np.ndarray, indices_h: np.ndarray, K: int, N: int, bu
             "host_cpus": os.cpu_count()}
 
 
+def reference_preprocess_baseline(indptr_h, indices_h, ours_ms, budget_nnz=3_000_000):
+    """The reference's OWN host preprocessing (voltrix::preprocess, bmat_kernels.cuh:264-320, compiled unmodified into
+    oracle/_ref; one host thread as in the reference) on a bounded row prefix, beside the GPU preprocessing of this run."""
+    import oracle
+    M = indptr_h.size - 1
+    rows = max(16, min(M, int(np.searchsorted(indptr_h, budget_nnz, side="right")) - 1) // 16 * 16)
+    ip = np.ascontiguousarray(indptr_h[: rows + 1])
+    ix = np.ascontiguousarray(indices_h[: ip[-1]])
+    ref = oracle.ref()
+    t0 = time.perf_counter()
+    ref.preprocess(ip, ix)
+    dt = time.perf_counter() - t0
+    nnz_s, nnz = int(ix.size), int(indices_h.size)
+    return {"kind": "reference (oracle/_ref: unmodified voltrix::preprocess, 1 host thread; stage a2 only, a3/a4 not included)",
+            "sample": f"rows [0,{rows}) ({nnz_s} of {nnz} nnz)", "sample_ms": dt * 1e3,
+            "extrapolated_whole_graph_ms": dt * 1e3 * nnz / max(nnz_s, 1),
+            "this_repo_gpu_csr_preprocess_ms_whole_graph": ours_ms}
+
+
 def extra_cpu_baselines(indptr_h, indices_h, K, N, budget_nnz=4_000_000):
     """scipy (1 thread) and torch.sparse CPU (all threads) on a smaller sample, as BASELINE.md lists them."""
     import scipy.sparse as sp
@@ -495,6 +514,10 @@ def run_product_arm(args):
             line["cpu_baseline"] = cpu_baseline(ip_h, ix_h, M, N)
             if not args.no_baselines:
                 line["cpu_baseline"]["others"] = extra_cpu_baselines(ip_h, ix_h, M, N)
+                try:
+                    line["cpu_baseline"]["reference_preprocess"] = reference_preprocess_baseline(ip_h, ix_h, t_pre * 1e3)
+                except Exception as ex:
+                    line["cpu_baseline"]["reference_preprocess"] = {"error": str(ex)[:160]}
         except Exception as ex:
             line["cpu_baseline"] = {"error": str(ex)[:200]}
     emit(line)

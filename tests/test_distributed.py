@@ -97,3 +97,26 @@ def test_sharded_spmm_gloo_world2():
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in results)
     assert results[0][2] == results[1][2], "every rank must compute the same partition"
+
+
+def test_row_cost_balances_skewed_row_counts():
+    """R-MAT-like skew: a dense head (few rows, many non-zeros each) and a long sparse tail.  Equal-nnz shards give the
+    tail rank 6x the rows of the head rank; with the per-row cost (ROW_COST non-zeros per row: its share of the window's
+    work item and the C row write, measured on the 2-GPU R-MAT run) the modelled cost nnz + ROW_COST * rows is balanced."""
+    import torch
+    from voltrix.distributed import ROW_COST, partition_rows
+    g = torch.Generator().manual_seed(0)
+    head = torch.randint(80, 120, (30_000,), generator=g)
+    tail = torch.randint(0, 4, (1_500_000,), generator=g)
+    deg = torch.cat([head, tail])
+
+    def costs(ranges):
+        return [int(deg[a:b].sum()) + ROW_COST * (b - a) for a, b in ranges]
+
+    by_nnz = costs(partition_rows(deg, 4))
+    by_cost = costs(partition_rows(deg + ROW_COST, 4))
+    assert max(by_cost) / (sum(by_cost) / 4) < 1.01
+    assert max(by_nnz) / (sum(by_nnz) / 4) > 1.5
+    rng = partition_rows(deg + ROW_COST, 4)
+    assert rng[0][0] == 0 and rng[-1][1] == deg.numel() and all(a % 16 == 0 for a, _ in rng)
+    assert all(rng[k][1] == rng[k + 1][0] for k in range(3))

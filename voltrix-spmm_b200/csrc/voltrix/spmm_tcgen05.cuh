@@ -15,18 +15,24 @@
 //   * D^T lives in TMEM (128 lanes x 16 fp32 columns, double buffered across work items) and is read
 //     back with tcgen05.ld 32x32b: a thread holds the 16 window rows of one feature, so every store
 //     instruction of a warp writes 32 consecutive floats of one C row;
-//   * a K-step is 16 gathered rows (two TC blocks); a pipeline stage is 4 K-steps (16 KB of B rows + 2 KB
-//     of A^T), so the MMA warp pays one mbarrier wait and one tcgen05.commit per 64 gathered rows;
-//   * warp roles (10 warps): 0-3 producers -- warp w owns K-step w of every stage: it expands the two
-//     bitmaps into the A^T tile with all 32 lanes, then ONE elected lane issues the 8 gather4 copies
-//     (elect.sync keeps the TMA operands in uniform registers: no per-lane serialisation loop);
-//     4-7 epilogue (TMEM lane quarter = warp % 4); 8 = MMA issuer + TMEM owner; 9 = metadata loader,
-//     which streams each item's hind / bitmap arrays into a shared-memory ring with 1-D bulk copies so
-//     the producers never wait on a global load;
+//   * a K-step is 16 gathered rows (two TC blocks); a pipeline stage is NPW K-steps (one per producer warp: 12 x (4 KB of
+//     B rows + 512 B of A^T) in the 36/12 variant), so the MMA warp pays one mbarrier wait and one tcgen05.commit per stage;
+//   * warp roles (NPW + 6 warps): 0..NPW-1 producers -- warp w owns K-step w of every stage: it expands the two bitmaps
+//     into the A^T tile with all 32 lanes (nibble table in shared memory, one STS.128 per lane), then ONE elected lane
+//     issues the 8 gather4 copies (elect.sync keeps the TMA operands in uniform registers: no per-lane serialisation
+//     loop); next 4 warps = epilogue (TMEM lane quarter = warp % 4); then the MMA issuer + TMEM owner; then the metadata
+//     loader, which streams each item's hind / bitmap arrays into a shared-memory ring with 1-D bulk copies so the
+//     producers never wait on a global load;
 //   * full/empty mbarriers per stage (tcgen05.commit frees a stage when the MMAs that read it retire),
 //     full/empty per metadata chunk, full/empty per TMEM accumulator;
 //   * persistent CTAs stride over the LPT-sorted work list (schedule.cuh), every role derives the same
-//     item sequence independently, so no intra-CTA work broadcast is needed.
+//     item sequence independently, so no intra-CTA work broadcast is needed;
+//   * TERMS = 2 (fp32 input as two bf16 terms) doubles the gathered tile and the MMAs of a K-step, same accumulator;
+//   * the optional Epilogue (row scale / bias / ReLU) is applied to whole-window items here and to K-split windows in
+//     vx_fixup_kernel.
+// What paces it (measured, profiles/r1c_bottleneck_isolation.md): a 128x16x16 MMA costs ~68 clk back to back, TMA writes 32
+// and the tensor core reads 36 shared-memory wavefronts per K-step, and the L2 slices deliver the gather at 86 % of their
+// peak at best -- three floors of 61-68 clk per K-step; the kernel runs at ~79.
 #ifndef VOLTRIX_B200_SPMM_TCGEN05_CUH_
 #define VOLTRIX_B200_SPMM_TCGEN05_CUH_
 
