@@ -1,68 +1,94 @@
 """Loaded JIT artefacts.
 
-A ``Runtime`` is a cache directory ``kernel.<name>.<hash>/{kernel.cu,kernel.args,kernel.so}`` whose
-``kernel.so`` exports ``launch`` (same layout and call protocol as the reference,
-voltrix/jit/runtime.py:9-72).  Calling it marshals the arguments with ctypes, passes a trailing
-``int&`` and returns its value: 0 on success, a VX_* error code otherwise.
+An artefact is a directory ``kernel.<name>.<hash>/`` holding ``kernel.cu`` (generated source), ``kernel.args`` (the
+``arg_defs`` as a Python literal) and ``kernel.so`` (exports ``extern "C" void launch(..., int& __return_code)``) -- the
+layout and call protocol of the reference (voltrix/jit/runtime.py:9-72).  ``Runtime(path)(*args)`` checks the arguments
+against ``kernel.args``, marshals them through ctypes and returns the code the kernel wrote: 0, or a VX_* error.
 """
+import ast
 import ctypes
 import os
-from typing import Optional
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 
 from .template import map_ctype
 
+_ARTEFACT_FILES = ("kernel.cu", "kernel.args", "kernel.so")
+# names that may appear in kernel.args (written by compiler.build from template.typename_map)
+_ARG_NAMESPACE = {"torch": torch, "int": int, "bool": bool, "float": float}
+
+
+def _read_arg_defs(path: str) -> Tuple[Tuple[str, object], ...]:
+    """kernel.args is ``(('name', type), ...)``; a single-argument kernel writes one bare pair."""
+    with open(path, "r") as fh:
+        text = fh.read()
+    ast.parse(text, mode="eval")                      # a literal expression, nothing else
+    defs = eval(text, {"__builtins__": {}}, dict(_ARG_NAMESPACE))  # noqa: S307
+    if defs and not isinstance(defs[0], tuple):
+        defs = (defs,)
+    return tuple(defs)
+
 
 class Runtime:
-    FILES = ("kernel.cu", "kernel.args", "kernel.so")
-
     def __init__(self, path: str) -> None:
+        if not self.is_path_valid(path):
+            raise AssertionError(f"{path} is not a complete JIT artefact")
         self.path = path
-        self.lib = None
-        self.args = None
-        assert self.is_path_valid(self.path), f"{path} is not a complete JIT artefact"
+        self._lib = None
+        self._launch = None
+        self._arg_defs: Optional[Tuple[Tuple[str, object], ...]] = None
 
     @staticmethod
     def is_path_valid(path: str) -> bool:
-        return os.path.isdir(path) and all(os.path.exists(os.path.join(path, f)) for f in Runtime.FILES)
+        return os.path.isdir(path) and all(os.path.isfile(os.path.join(path, name)) for name in _ARTEFACT_FILES)
 
-    def _load(self) -> None:
-        self.lib = ctypes.CDLL(os.path.join(self.path, "kernel.so"))
-        with open(os.path.join(self.path, "kernel.args"), "r") as f:
-            self.args = eval(f.read())  # noqa: S307 -- written by build(); a tuple list of (name, type)
-        if self.args and not isinstance(self.args[0], tuple):
-            self.args = (self.args,)  # single-argument kernels: "('x', int)" evals to one tuple
+    # kept for callers that poke at the loaded state like the reference's tests do
+    @property
+    def lib(self):
+        return self._lib
 
-    def __call__(self, *args) -> int:
-        if self.lib is None or self.args is None:
-            self._load()
-        assert len(args) == len(self.args), f"Expected {len(self.args)} arguments, got {len(args)}"
-        cargs = []
-        for arg, (name, dtype) in zip(args, self.args):
-            if arg is None:
-                pass  # optional tensor -> null pointer
-            elif isinstance(arg, torch.Tensor):
-                assert arg.dtype == dtype, f"Expected tensor dtype `{dtype}` for `{name}`, got `{arg.dtype}`"
-            else:
-                assert isinstance(arg, dtype), f"Expected built-in type `{dtype}` for `{name}`, got `{type(arg)}`"
-            cargs.append(map_ctype(arg, dtype))
-        return_code = ctypes.c_int(0)
-        self.lib.launch(*cargs, ctypes.byref(return_code))
-        return return_code.value
+    @property
+    def args(self):
+        return self._arg_defs
+
+    def _ensure_loaded(self) -> None:
+        if self._launch is None:
+            self._lib = ctypes.CDLL(os.path.join(self.path, "kernel.so"))
+            self._launch = self._lib.launch
+            self._arg_defs = _read_arg_defs(os.path.join(self.path, "kernel.args"))
+
+    def _marshal(self, values: Sequence) -> list:
+        if len(values) != len(self._arg_defs):
+            raise AssertionError(f"Expected {len(self._arg_defs)} arguments, got {len(values)}")
+        out = []
+        for value, (name, declared) in zip(values, self._arg_defs):
+            if isinstance(value, torch.Tensor):
+                if value.dtype != declared:
+                    raise AssertionError(f"Expected tensor dtype `{declared}` for `{name}`, got `{value.dtype}`")
+            elif value is not None and not isinstance(value, declared):   # None = null pointer for an optional tensor
+                raise AssertionError(f"Expected built-in type `{declared}` for `{name}`, got `{type(value)}`")
+            out.append(map_ctype(value, declared))
+        return out
+
+    def __call__(self, *values) -> int:
+        self._ensure_loaded()
+        code = ctypes.c_int(0)
+        self._launch(*self._marshal(values), ctypes.byref(code))
+        return code.value
 
 
 class RuntimeCache:
+    """path -> Runtime; a path that is not (yet) a complete artefact maps to None."""
+
     def __init__(self) -> None:
-        self.cache = {}
+        self._by_path: Dict[str, Runtime] = {}
 
     def __getitem__(self, path: str) -> Optional[Runtime]:
-        if path in self.cache:
-            return self.cache[path]
-        if Runtime.is_path_valid(path):
-            self.cache[path] = Runtime(path)
-            return self.cache[path]
-        return None
+        hit = self._by_path.get(path)
+        if hit is None and Runtime.is_path_valid(path):
+            hit = self._by_path[path] = Runtime(path)
+        return hit
 
     def __setitem__(self, path: str, runtime: Runtime) -> None:
-        self.cache[path] = runtime
+        self._by_path[path] = runtime

@@ -29,3 +29,23 @@ def ws_units(nbytes: int) -> int:
 
 def alloc_workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(ws_units(nbytes) * WS_UNIT, dtype=torch.uint8, device=device)
+
+
+def expect_cuda(**tensors) -> None:
+    """``expect_cuda(name=(tensor, dtype), ...)``: every operand of a kernel wrapper lives on the GPU with the dtype the
+    native entry point casts its pointer to (the reference asserts the same, one line per operand)."""
+    for name, (t, dtype) in tensors.items():
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype):
+            got = f"{t.dtype} on {t.device}" if isinstance(t, torch.Tensor) else type(t).__name__
+            raise AssertionError(f"`{name}` must be a CUDA tensor of dtype {dtype}, got {got}")
+
+
+def launch_untuned(name: str, includes: tuple, template: str, operands) -> None:
+    """Build (or fetch) the single variant of a kernel that has no tuning space and run it on the current stream.
+    ``operands``: ordered ``(arg name, declared type, value)`` triples -- the ``launch`` signature and the call in one."""
+    from .tuner import jit_tuner
+    operands = tuple(operands) + (("stream", torch.cuda.Stream, current_stream()),)
+    values = tuple(v for _, _, v in operands)
+    runtime = jit_tuner.compile_and_tune(name=name, keys={}, space=tuple(), includes=includes,
+                                         arg_defs=tuple((n, t) for n, t, _ in operands), template=template, args=values)
+    check(runtime(*values), name)

@@ -5,8 +5,7 @@ Reference: voltrix/jit_kernels/bmat_swizzle.py:14-48 -> voltrix::hmat_packed_swi
 """
 import torch
 
-from ._common import check, current_stream
-from .tuner import jit_tuner
+from ._common import expect_cuda, launch_untuned
 
 includes = ('"voltrix/bmat_kernels.cuh"',)
 template = """
@@ -14,32 +13,13 @@ __return_code = voltrix::hmat_packed_swizzle_cuda(num_row_windows, pointer1, hsp
 """
 
 
-def hmat_packed_swizzle_kernel(
-    block_partition: torch.Tensor,
-    pointer1: torch.Tensor,
-    hspa: torch.Tensor,
-    hspa_packed: torch.Tensor,
-):
-    assert block_partition.is_cuda and block_partition.dtype == torch.int32
-    assert pointer1.is_cuda and pointer1.dtype == torch.int32
-    assert hspa.is_cuda and hspa.dtype == torch.float
-    assert hspa_packed.is_cuda and hspa_packed.dtype == torch.uint32
+def swizzle_arg_defs():
+    return (("num_row_windows", int), ("pointer1", torch.int32), ("hspa", torch.float32), ("hspa_packed", torch.uint32))
 
-    num_row_windows = block_partition.shape[0]
-    args = (num_row_windows, pointer1, hspa, hspa_packed, current_stream())
-    runtime = jit_tuner.compile_and_tune(
-        name="hmat_packed_swizzle_kernel",
-        keys={},
-        space=tuple(),
-        includes=includes,
-        arg_defs=(
-            ("num_row_windows", int),
-            ("pointer1", torch.int),
-            ("hspa", torch.float),
-            ("hspa_packed", torch.uint32),
-            ("stream", torch.cuda.Stream),
-        ),
-        template=template,
-        args=args,
-    )
-    check(runtime(*args), "hmat_packed_swizzle_kernel")
+
+def hmat_packed_swizzle_kernel(block_partition: torch.Tensor, pointer1: torch.Tensor, hspa: torch.Tensor,
+                               hspa_packed: torch.Tensor):
+    expect_cuda(block_partition=(block_partition, torch.int32), pointer1=(pointer1, torch.int32),
+                hspa=(hspa, torch.float32), hspa_packed=(hspa_packed, torch.uint32))
+    values = dict(num_row_windows=int(block_partition.shape[0]), pointer1=pointer1, hspa=hspa, hspa_packed=hspa_packed)
+    launch_untuned("hmat_packed_swizzle_kernel", includes, template, [(n, t, values[n]) for n, t in swizzle_arg_defs()])

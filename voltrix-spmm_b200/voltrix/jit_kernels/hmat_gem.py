@@ -7,60 +7,31 @@ window per TC block; runs on the current stream.
 """
 import torch
 
-from ._common import check, current_stream
-from .tuner import jit_tuner
+from ._common import expect_cuda, launch_untuned
 
 includes = ('"voltrix/bmat_kernels.cuh"',)
 template = """
 __return_code = voltrix::hmat_cuda(node_pointer, edge_list, block_partition, edge_to_column, edge_to_row, pointer1,
                                    num_row_windows, num_nodes, (int64_t)num_edges, hspa, hind, stream);
 """
+_I32, _F32 = torch.int32, torch.float32
 
 
-def hmat_gen_kernel(
-    node_pointer: torch.Tensor,
-    edge_list: torch.Tensor,
-    block_partition: torch.Tensor,
-    edge_to_column: torch.Tensor,
-    edge_to_row: torch.Tensor,
-    pointer1: torch.Tensor,
-    hspa: torch.Tensor,
-    hind: torch.Tensor,
-):
-    assert node_pointer.is_cuda and node_pointer.dtype == torch.int32
-    assert edge_list.is_cuda and edge_list.dtype == torch.int32
-    assert block_partition.is_cuda and block_partition.dtype == torch.int32
-    assert edge_to_column.is_cuda and edge_to_column.dtype == torch.int32
-    assert edge_to_row.is_cuda and edge_to_row.dtype == torch.int32
-    assert pointer1.is_cuda and pointer1.dtype == torch.int32
-    assert hspa.is_cuda and hspa.dtype == torch.float
-    assert hind.is_cuda and hind.dtype == torch.int32
+def hmat_arg_defs():
+    """``launch`` signature without the trailing stream (used by the prebuild step, which has no operands)."""
+    ints = ("node_pointer", "edge_list", "block_partition", "edge_to_column", "edge_to_row", "pointer1")
+    return tuple((n, _I32) for n in ints) + (("num_row_windows", int), ("num_nodes", int), ("num_edges", int),
+                                             ("hspa", _F32), ("hind", _I32))
 
-    num_row_windows = block_partition.shape[0]
-    num_nodes = node_pointer.shape[0] - 1
-    num_edges = edge_list.shape[0]
-    args = (node_pointer, edge_list, block_partition, edge_to_column, edge_to_row, pointer1, num_row_windows,
-            num_nodes, num_edges, hspa, hind, current_stream())
-    runtime = jit_tuner.compile_and_tune(
-        name="hmat_gen_kernel",
-        keys={},
-        space=tuple(),
-        includes=includes,
-        arg_defs=(
-            ("node_pointer", torch.int),
-            ("edge_list", torch.int),
-            ("block_partition", torch.int),
-            ("edge_to_column", torch.int),
-            ("edge_to_row", torch.int),
-            ("pointer1", torch.int),
-            ("num_row_windows", int),
-            ("num_nodes", int),
-            ("num_edges", int),
-            ("hspa", torch.float),
-            ("hind", torch.int),
-            ("stream", torch.cuda.Stream),
-        ),
-        template=template,
-        args=args,
-    )
-    check(runtime(*args), "hmat_gen_kernel")
+
+def hmat_gen_kernel(node_pointer: torch.Tensor, edge_list: torch.Tensor, block_partition: torch.Tensor,
+                    edge_to_column: torch.Tensor, edge_to_row: torch.Tensor, pointer1: torch.Tensor,
+                    hspa: torch.Tensor, hind: torch.Tensor):
+    tensors = dict(node_pointer=node_pointer, edge_list=edge_list, block_partition=block_partition,
+                   edge_to_column=edge_to_column, edge_to_row=edge_to_row, pointer1=pointer1, hspa=hspa, hind=hind)
+    sizes = dict(num_row_windows=int(block_partition.shape[0]), num_nodes=int(node_pointer.shape[0]) - 1,
+                 num_edges=int(edge_list.shape[0]))
+    defs = hmat_arg_defs()
+    expect_cuda(**{n: (tensors[n], t) for n, t in defs if n in tensors})
+    launch_untuned("hmat_gen_kernel", includes, template,
+                   [(n, t, tensors[n] if n in tensors else sizes[n]) for n, t in defs])

@@ -13,15 +13,11 @@ from .tuner import jit_tuner
 
 
 def _hmat_arg_defs():
-    return (("node_pointer", torch.int), ("edge_list", torch.int), ("block_partition", torch.int),
-            ("edge_to_column", torch.int), ("edge_to_row", torch.int), ("pointer1", torch.int),
-            ("num_row_windows", int), ("num_nodes", int), ("num_edges", int), ("hspa", torch.float),
-            ("hind", torch.int), ("stream", torch.cuda.Stream))
+    return hmat_gem.hmat_arg_defs() + (("stream", torch.cuda.Stream),)
 
 
 def _swizzle_arg_defs():
-    return (("num_row_windows", int), ("pointer1", torch.int), ("hspa", torch.float),
-            ("hspa_packed", torch.uint32), ("stream", torch.cuda.Stream))
+    return bmat_swizzle.swizzle_arg_defs() + (("stream", torch.cuda.Stream),)
 
 
 def all_variants():
