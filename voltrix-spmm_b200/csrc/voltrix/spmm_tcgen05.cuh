@@ -39,7 +39,7 @@
 #include "voltrix/common.cuh"
 #include "voltrix/ptx.cuh"
 
-// Bottleneck-isolation builds (scripts/gpu_isolate.sh; results are garbage, timing only):
+// Bottleneck-isolation builds (scripts/isolate.py; results are garbage, timing only):
 //   VX_TC_DBG=1  producers + TMA gather run, the MMA issuer only commits      -> gather path alone
 //   VX_TC_DBG=2  bitmap expansion + MMAs run on stale shared memory, no TMA   -> MMA operand reads alone
 #ifndef VX_TC_DBG
