@@ -444,7 +444,11 @@ def run_product_arm(args):
         e2e_serial_ms = time_e2e(serial_steps)
         log(f"[rank {rank}] e2e serial {e2e_serial_ms:.2f} ms/step; streamed leg ...")
         del feat_dev
-        pipe = voltrix.HostStreamedSpMM(blk, packed, hind, sh.local_rows, sh.local_nnz, N, dtype=feat.dtype, input_rows=M)
+        shard_upload = world > 1 and os.environ.get("VX_BENCH_E2E_SHARDED", "0") == "1"   # round-2 experiment, see DESIGN 8.1
+        pipe = voltrix.HostStreamedSpMM(blk, packed, hind, sh.local_rows, sh.local_nnz, N, dtype=feat.dtype, input_rows=M,
+                                        shard_upload=shard_upload)
+        if shard_upload:
+            h2d_b = int(feat_host.numel() * 2)
 
         def streamed_steps(n):
             pipe.fork()                                         # its streams start after the `s` event on this stream

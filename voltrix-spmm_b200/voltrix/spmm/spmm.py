@@ -249,13 +249,25 @@ class HostStreamedSpMM:
     """
 
     def __init__(self, blk_offsets, hspa_packed, hind, num_nodes: int, num_edges: int, num_feats: int,
-                 dtype=torch.float16, input_rows: Optional[int] = None, depth: int = 2):
+                 dtype=torch.float16, input_rows: Optional[int] = None, depth: int = 2, shard_upload: bool = False,
+                 group=None):
+        """``shard_upload`` (multi-GPU, one process per GPU, torch.distributed initialised): every rank uploads only its
+        1/world slice of the dense operand and the ranks all-gather it over NVLink (NCCL) instead of each pulling the whole
+        operand through the host's PCIe.  EXPERIMENTAL: written at the end of round 1 without GPU time left to run it;
+        off by default."""
         require_cuda()
         dev = hspa_packed.device
         self.state = (blk_offsets, hspa_packed, hind)
         self.num_nodes, self.num_edges, self.depth = num_nodes, num_edges, depth
         rows = input_rows if input_rows is not None else num_nodes
-        self.feat_dev = [torch.empty(rows, num_feats, dtype=dtype, device=dev) for _ in range(depth)]
+        self.rows = rows
+        self.group, self.world, self.rank = group, 1, 0
+        if shard_upload:
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size(group) > 1:
+                self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.chunk = (rows + self.world - 1) // self.world          # all-gather needs equal slices: pad the last one
+        self.feat_dev = [torch.empty(self.chunk * self.world, num_feats, dtype=dtype, device=dev) for _ in range(depth)]
         self.out_dev = [torch.empty(num_nodes, num_feats, dtype=torch.float32, device=dev) for _ in range(depth)]
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]      # feat_dev[b] filled
@@ -276,13 +288,22 @@ class HostStreamedSpMM:
         with torch.cuda.stream(self.s_in):
             if not first_use:
                 self.s_in.wait_event(self.ev_run[b])     # the kernel that read feat_dev[b] is done
-            self.feat_dev[b].copy_(feat_host, non_blocking=True)
+            if self.world == 1:
+                self.feat_dev[b].copy_(feat_host, non_blocking=True)
+            else:
+                import torch.distributed as dist
+                lo, hi = self.rank * self.chunk, min((self.rank + 1) * self.chunk, self.rows)
+                if hi > lo:
+                    self.feat_dev[b][lo:hi].copy_(feat_host[lo:hi], non_blocking=True)
+                mine = self.feat_dev[b][self.rank * self.chunk: (self.rank + 1) * self.chunk]
+                dist.all_gather_into_tensor(self.feat_dev[b], mine, group=self.group)   # in place, on s_in
             self.ev_in[b].record(self.s_in)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(self.ev_in[b])
             if not first_use:
                 self.s_run.wait_event(self.ev_out[b])    # out_dev[b] has been copied out
-            spmm(*self.state, self.num_nodes, self.num_edges, self.feat_dev[b], out=self.out_dev[b])
+            operand = self.feat_dev[b] if self.world == 1 else self.feat_dev[b][: self.rows]   # drop the all-gather padding
+            spmm(*self.state, self.num_nodes, self.num_edges, operand, out=self.out_dev[b])
             self.ev_run[b].record(self.s_run)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_run[b])
