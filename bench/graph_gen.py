@@ -11,8 +11,8 @@ What differs: the reference loads `<base_folder>/<data_name>.npz` through TC-GNN
 datasets (and no network) here, so `--data_name` selects a synthetic graph of the same (M, nnz) shape from
 voltrix.graphs (`reddit`, `ddi`, `products`, `rmat<scale>`, `uniform:<M>:<nnz>` ...).  If
 `<base_folder>/<data_name>.npz` does exist it is loaded (keys `src_li`/`dst_li`/`num_nodes`, the TC-GNN layout).
-`--seed` is honoured (the reference parses it and ignores it).  `--reorder` applies a degree-sort
-relabelling (stand-in for the offline TCA reordering, which needs libraries that are not installed).
+`--seed` is honoured (the reference parses it and ignores it).  `--reorder` relabels the nodes with
+voltrix.reorder.lsh_reorder (min-hash LSH on the GPU -- the role DTC-SpMM's offline TCA_reorder.py plays for the reference).
 """
 import argparse
 import os
@@ -46,13 +46,8 @@ def load_graph(args, device):
     else:
         ip, ix = graphs.suite_graph(name, seed=args.seed, device=device)
     if args.reorder:
-        M = ip.numel() - 1
-        deg = ip[1:] - ip[:-1]
-        perm = torch.argsort(deg, descending=True, stable=True)          # new id -> old id
-        inv = torch.empty_like(perm); inv[perm] = torch.arange(M, device=perm.device)
-        rows = torch.repeat_interleave(torch.arange(M, device=ip.device), deg.long())
-        keys = (inv[rows].long() << 32) | inv[ix.long()].long()
-        ip, ix = graphs._csr_from_keys(keys, M, 32)
+        from voltrix import reorder
+        ip, ix = reorder.permute_graph(ip, ix, reorder.lsh_reorder(ip, ix, seed=args.seed))
     return ip, ix
 
 
