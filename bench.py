@@ -474,6 +474,12 @@ def run_product_arm(args):
     gather_bytes = (plan.total_blocks * 8 * N * 2 + 48 * plan.total_blocks + sh.local_rows * N * 4)
     traffic, traffic_src = measured_traffic({k: v for k, v in tuned.items() if k[0] == "spmm_kernel"}, args.workload) \
         if world == 1 and args.scale == 1.0 else (None, None)
+    # measured floors of the tensor-core kernel on THIS workload (timing-only builds, profiles/r1c_bottleneck_isolation.md):
+    # what actually bounds the launch when B is L2-resident and the compulsory-HBM fraction is structurally ~5 %
+    floors = None
+    if args.workload == "reddit" and args.scale == 1.0 and world == 1:
+        floors = {"l2_slices_to_sm_gather_ms": 1.48, "tcgen05_mma_issue_ms": 1.65, "shared_memory_port_ms": 1.64,
+                  "frac_of_binding_floor": 1.65 / ms, "source": "profiles/r1c_bottleneck_isolation.md"}
     launches_per_step = 1 + (1 if plan.num_sparse_rows else 0) + (1 if plan.num_fixups else 0)
     line = {
         "metric": METRIC if N == 128 else METRIC.replace("N=128", f"N={N}"),
@@ -488,6 +494,7 @@ def run_product_arm(args):
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "alg_bytes_per_launch": abytes_local,
                      "alg_bytes_whole_job": abytes,
                      "gather_bytes_per_launch": gather_bytes, "gather_gbs": gather_bytes / (ms * 1e-3) / 1e9,
+                     "kernel_floors": floors,
                      "note": (f"B ({M * N * 2 / 1e6:.1f} MB fp16) is L2-resident: the kernel is bound by the L2->SM gather "
                               "stream (gather_bytes), not by compulsory HBM bytes -- see DESIGN.md section 4.5")
                      if M * N * 2 < 100e6 else
