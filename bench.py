@@ -65,7 +65,7 @@ def measured_traffic(tuned: dict, workload: str):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), if this run uses the
     kernel variant and workload that capture was taken on; else None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1b_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             db = json.load(f)
         for v in tuned.values():
             key = f"vx_spmm_tc_kernel<__half,{v['stages']},{v['npw']}>|{workload}"
@@ -270,6 +270,12 @@ def ref_kernel_baseline(blk, packed, hind, M, nnz, N, feat16, iters=3):
 
 
 # ------------------------------------------------------------------------------------------- arms
+def workload_config(desc: str, M: int, nnz: int, N: int) -> dict:
+    """The `config` object, identical in both arms (the driver compares them)."""
+    return {"workload": desc, "M": M, "nnz": nnz, "N": N,
+            "l2": "GPU arm: flushed (256 MB write) before every timed step; CPU arm: operands exceed the host caches"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -305,7 +311,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "sample": sample},
+            "config": workload_config(desc, M, int(indices_h.size), N),
             "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": c.num_threads(), "kind": "port", "sample": sample,
                              "host_cpus": os.cpu_count(),
                              "note": "the reference ships no CPU SpMM; oracle/voltrix_oracle.c vo_spmm_csr (OpenMP)"},
@@ -314,40 +320,92 @@ def run_reference_arm(args):
     emit(line)
 
 
-def run_product_arm(args):
-    import faulthandler
+def build_sharded(workload: str, scale: float, dev, world: int):
+    """(ShardedSpMM, whole-graph indptr/indices or None, M, nnz, N, description).  The R-MAT of C5 is never materialised
+    on one rank when the job is sharded: every rank replays the same seeded edge stream twice -- once for the row
+    histogram the partition needs, once keeping only its own rows."""
+    from voltrix import graphs
+    from voltrix.distributed import ROW_COST, ShardedSpMM
+    if workload == "rmat25" and world > 1:
+        sc = 25 if scale >= 1 else max(12, int(25 + np.log2(scale)))
+        hist = graphs.rmat_row_histogram(sc, 32, seed=0, device=dev)          # draws per row (before coalescing)
+        sh = ShardedSpMM(None, None, 1 << sc, weights=hist + ROW_COST,
+                         local_csr=lambda r0, r1: graphs.rmat_csr(sc, 32, seed=0, device=dev, row_range=(r0, r1)))
+        del hist
+        nnz_t = torch.tensor([sh.local_nnz], device=dev, dtype=torch.int64)
+        import torch.distributed as dist
+        dist.all_reduce(nnz_t)
+        return sh, None, None, 1 << sc, int(nnz_t.item()), 256, \
+            f"R-MAT scale {sc} (0.57,0.19,0.19,0.05) edge factor 32, N=256 fp16"
+    indptr, indices, N, desc = make_workload(workload, dev, scale)   # same seeded graph on every rank
+    M = indptr.numel() - 1
+    return ShardedSpMM(indptr, indices, M), indptr, indices, M, indices.numel(), N, desc
+
+
+def parity_check(indptr_h, indices_h, row0, feat, out_rows, budget_nnz: int, ncols: int):
+    """The timed GPU result against the CPU oracle (vo_spmm_csr, fp32 sums of the same fp16-rounded operand) on a bounded
+    row prefix of rank 0's shard: the comparison of the reference's tests/test_spmm.py:75-96, inside the bench run.
+    ``indptr_h`` / ``indices_h``: the CSR rows the GPU result covers (local numbering); ``out_rows``: GPU C, same rows."""
+    import oracle
+    from voltrix.utils import calc_diff, relative_error
+    c = oracle.c()
+    c.set_num_threads(os.cpu_count() or 1)
+    M = indptr_h.size - 1
+    rows = max(1, min(M, int(np.searchsorted(indptr_h, budget_nnz, side="right")) - 1))
+    B = feat[:, :ncols].float().cpu().numpy()     # output columns are independent: a column slice is a valid check
+    want = torch.from_numpy(c.spmm_csr(indptr_h, indices_h, B, 0, rows, assume_coalesced=True))
+    got = out_rows[:rows, :ncols].float().cpu()
+    scale = max(float(want.abs().max()), 1e-9)
+    err = float((got - want).abs().max()) / scale
+    cd = float(calc_diff(got, want))
+    rel = float(relative_error(got, want))
+    return {"rows_checked": rows, "first_row": row0, "cols_checked": ncols, "nnz_checked": int(indptr_h[rows]),
+            "max_scaled_err": err,
+            "calc_diff": cd, "difference_rate_pct": f"{cd * 100:.2f}", "relative_error": rel,
+            "ok": bool(err <= 1e-4 and rel <= 1e-2 and f"{cd * 100:.2f}" in ("0.00", "-0.00")),
+            "oracle": "oracle/voltrix_oracle.c vo_spmm_csr on the same fp16-rounded operand"}
+
+
+def committed_floors(workload: str, scale: float, world: int, ms: float):
+    """Measured floors of the tensor-core kernel (timing-only builds) from the committed report, if it covers this run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "floors.json")) as f:
+            db = json.load(f)
+        e = db.get(workload)
+        if e is None or scale != 1.0 or world != 1:
+            return None
+        out = dict(e)
+        out["frac_of_binding_floor"] = max(v for k, v in e.items() if k.endswith("_ms")) / ms
+        return out
+    except Exception:
+        return None
+
+
+def measure(workload: str, args, world: int, rank: int, dev, headline: bool, steps: int, warmup: int):
+    """One workload, all ranks: generate, shard, preprocess, time `steps` SpMMs (device events, L2 flushed, max over
+    ranks), check the timed result against the oracle, and (headline or small operands) the end-to-end leg."""
     import torch.distributed as dist
-    # hang diagnosis: dump every thread's Python stack to stderr if the bench is still running after this long
-    faulthandler.dump_traceback_later(int(os.environ.get("VX_BENCH_STACK_DUMP_S", "900")), repeat=False, exit=False)
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py (product arm) needs a GPU: there is no CPU fallback"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import datetime
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # a rank that stops making progress fails the collective after VX_BENCH_NCCL_TIMEOUT_S instead of 10 minutes
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(
-            seconds=int(os.environ.get("VX_BENCH_NCCL_TIMEOUT_S", "300"))))
     import voltrix
-    from voltrix.distributed import ShardedSpMM
 
     t_gen = time.perf_counter()
-    indptr, indices, N, desc = make_workload(args.workload, dev, args.scale)   # same seeded graph on every rank
-    M, nnz = indptr.numel() - 1, indices.numel()
+    sh, indptr, indices, M, nnz, N, desc = build_sharded(workload, args.scale, dev, world)
     torch.cuda.synchronize()
-    log(f"[rank {rank}] graph: M={M} nnz={nnz} N={N} ({time.perf_counter() - t_gen:.1f}s)")
-
-    # --- preprocessing (timed separately, excluded from the step like bench/bm_voltrix.py:17 vs :36) ---
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    sh = ShardedSpMM(indptr, indices, M)
-    torch.cuda.synchronize(); t_pre = time.perf_counter() - t0
+    log(f"[rank {rank}] {workload}: M={M} nnz={nnz} N={N} generated + preprocessed in {time.perf_counter() - t_gen:.1f}s")
     blk, packed, hind = sh.state
     plan = packed._vx_plan
+    # preprocessing alone, timed on a second pass when the whole graph is at hand (excluded from the step, like
+    # bench/bm_voltrix.py:17 vs :36)
+    t_pre = None
+    if indptr is not None and headline:
+        from voltrix.distributed import shard_csr
+        lp, li = shard_csr(indptr, indices, sh.r0, sh.r1)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        voltrix.csr_preprocess(lp, li, sh.local_rows, num_cols=M)
+        torch.cuda.synchronize(); t_pre = time.perf_counter() - t0
+        del lp, li
     log(f"[rank {rank}] rows [{sh.r0},{sh.r1}) nnz={sh.local_nnz} TCB={plan.total_blocks} items={plan.num_items} "
-        f"sparse_rows={plan.num_sparse_rows} fixups={plan.num_fixups} preprocess={t_pre * 1e3:.1f} ms")
+        f"sparse_rows={plan.num_sparse_rows} fixups={plan.num_fixups}"
+        + (f" preprocess={t_pre * 1e3:.1f} ms" if t_pre else ""))
 
     # --- dense operand: created on rank 0, broadcast over NCCL (the path's one exchange step) ---
     g = torch.Generator(device=dev).manual_seed(0)
@@ -364,7 +422,8 @@ def run_product_arm(args):
         return voltrix.spmm(blk, packed, hind, sh.local_rows, sh.local_nnz, feat, out=out)
 
     step(); torch.cuda.synchronize()     # autotune + JIT load
-    tuned = voltrix.jit_tuner.tuned_keys
+    tuned = {str(k): v for k, v in voltrix.jit_tuner.tuned_keys.items()
+             if k[0] == "spmm_kernel" and f"'N': {N}" in k[1] and "feature_hash" in k[1]}
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -373,57 +432,73 @@ def run_product_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         flush.zero_(); step()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    with clocks:
         barrier(); t_wall = time.perf_counter()
-        for i in range(args.steps):
+        for i in range(steps):
             flush.zero_()
             starts[i].record(); step(); ends[i].record()
         barrier(); t_wall = time.perf_counter() - t_wall
-        # keep the sampler alive over ~1.5 s of back-to-back steps so nvidia-smi sees the kernel under load
-        t_end = time.perf_counter() + 1.5
-        while time.perf_counter() < t_end:
-            for _ in range(20):
-                step()
-            torch.cuda.synchronize()
-    faulthandler.cancel_dump_traceback_later()
-    faulthandler.dump_traceback_later(int(os.environ.get("VX_BENCH_STACK_DUMP_S", "900")), repeat=False, exit=False)
+        if headline:
+            # keep the sampler alive over ~1.5 s of back-to-back steps so nvidia-smi sees the kernel under load
+            t_end = time.perf_counter() + 1.5
+            while time.perf_counter() < t_end:
+                for _ in range(20):
+                    step()
+                torch.cuda.synchronize()
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    log(f"[rank {rank}] timed loop done: {np.mean(step_ms):.3f} ms/step")
     ms = float(np.mean(step_ms))
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    log(f"[rank {rank}] {workload}: timed loop done: {ms:.3f} ms/step")
+    per_rank = torch.zeros(world, device=dev, dtype=torch.float64)
+    per_rank[rank] = ms
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+        dist.all_reduce(per_rank)
+    per_rank_ms = [float(v) for v in per_rank.tolist()]
+    ms_max = max(per_rank_ms)
+
+    # --- parity of the TIMED result (rank 0's rows) against the CPU oracle, bounded ---
+    parity = None
+    if rank == 0:
+        try:
+            flush.zero_(); step(); torch.cuda.synchronize()
+            if indptr is not None:
+                lo = int(indptr[sh.r0])
+                budget = 150_000_000      # the whole shard on C2 / C4 (~0.5-1 s of host time)
+                rows_cap = int(torch.searchsorted(indptr[sh.r0:sh.r1 + 1] - lo, budget).item())
+                rows_cap = max(1, min(sh.local_rows, rows_cap + 1))
+                ip_h = (indptr[sh.r0:sh.r0 + rows_cap + 1] - lo).cpu().numpy().astype(np.int32)
+                ix_h = indices[lo:lo + int(ip_h[-1])].cpu().numpy()
+            else:
+                ip_h, ix_h = plan.csr_indptr.cpu().numpy(), None
+                rows_cap = max(1, min(sh.local_rows, int(np.searchsorted(ip_h, 50_000_000))))
+                ip_h = np.ascontiguousarray(ip_h[: rows_cap + 1])
+                ix_h = plan.csr_indices[: int(ip_h[-1])].cpu().numpy()
+            parity = parity_check(ip_h, ix_h, sh.r0, feat, out, budget_nnz=int(ip_h[-1]),
+                                  ncols=N if M * N * 4 <= (4 << 30) else 32)
+            log(f"[rank 0] {workload}: parity {parity}")
+        except Exception as ex:
+            parity = {"error": str(ex)[:200], "ok": False}
 
     # --- e2e: public API with host buffers; H2D of B and D2H of C inside the timed region, every step ---
-    # (a) serial: copy-in, voltrix.spmm, copy-out on one stream.  (b) streamed: voltrix.HostStreamedSpMM runs the
-    # same three legs of consecutive steps on three streams (double-buffered), so PCIe in, the kernel and PCIe out
-    # overlap; every step still moves its own B and its own C.  The reported e2e value is (b).
-    # Rank-INVARIANT decision (every rank must take the same branch: the legs below contain barriers): every rank pins a
-    # full copy of B plus two buffers for its shard of C; on the 1B-nnz R-MAT that is 17 GB x 8 of page-locked memory.
-    e2e_bytes = world * M * N * 2 + 2 * M * N * 4
-    e2e_skipped = None
-    if e2e_bytes > (8 << 30):
-        e2e_skipped = f"skipped: {e2e_bytes / 2**30:.0f} GiB of pinned host memory over {world} rank(s)"
-        e2e_ms = e2e_serial_ms = float("nan")
-        e2e_ok = None
-        h2d_b = d2h_b = 0
+    # voltrix.HostStreamedSpMM runs copy-in, kernel and copy-out of consecutive steps on three streams (double-buffered).
+    # Multi-GPU: every rank uploads only ITS 1/world row slice of B from pinned host memory and the ranks all-gather the
+    # slices over NVLink (NCCL) on the copy-in stream -- B crosses the host links once per step, not once per rank -- and
+    # every rank reads back its own rows of C.
+    # Rank-INVARIANT decision (every rank takes the same branch: the legs below contain barriers).
+    e2e_bytes = world * M * N * 2 + 2 * M * N * 4     # every rank pins B; C shards are pinned twice (double buffer)
+    e2e = {"value": None, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    flops = 2.0 * nnz * N
+    if e2e_bytes > (8 << 30) or not (headline or args.e2e_extras):
+        e2e["skipped"] = (f"{e2e_bytes / 2**30:.0f} GiB of pinned host memory over {world} rank(s)" if e2e_bytes > (8 << 30)
+                          else "extra workload: device-timed only")
     else:
-        feat_host = feat.cpu().pin_memory()
+        host_view = feat.cpu().pin_memory()     # the caller's B in pinned host memory (each rank reads only its slice)
         out_host = [torch.empty(sh.local_rows, N, dtype=torch.float32).pin_memory() for _ in range(2)]
-        feat_dev = torch.empty_like(feat)
-        h2d_b, d2h_b = int(feat_host.numel() * 2) * world, int(out_host[0].numel() * 4) * world
-
-        def e2e_serial_step():
-            feat_dev.copy_(feat_host, non_blocking=True)
-            o = voltrix.spmm(blk, packed, hind, sh.local_rows, sh.local_nnz, feat_dev, out=out)
-            out_host[0].copy_(o, non_blocking=True)
-
-        n_e2e = max(3, min(args.steps, 10))
+        n_e2e = max(3, min(steps, 10))
 
         def time_e2e(run_steps):
             run_steps(2)
@@ -436,104 +511,187 @@ def run_product_arm(args):
                 dist.all_reduce(t2, op=dist.ReduceOp.MAX)
             return float(t2.item())
 
-        def serial_steps(n):
-            for _ in range(n):
-                e2e_serial_step()
+        e2e_serial_ms = None
+        if world == 1:
+            feat_dev = torch.empty_like(feat)
 
-        log(f"[rank {rank}] e2e serial leg ...")
-        e2e_serial_ms = time_e2e(serial_steps)
-        log(f"[rank {rank}] e2e serial {e2e_serial_ms:.2f} ms/step; streamed leg ...")
-        del feat_dev
-        shard_upload = world > 1 and os.environ.get("VX_BENCH_E2E_SHARDED", "0") == "1"   # round-2 experiment, see DESIGN 8.1
-        pipe = voltrix.HostStreamedSpMM(blk, packed, hind, sh.local_rows, sh.local_nnz, N, dtype=feat.dtype, input_rows=M,
-                                        shard_upload=shard_upload)
-        if shard_upload:
-            h2d_b = int(feat_host.numel() * 2)
+            def serial_steps(n):
+                for _ in range(n):
+                    feat_dev.copy_(host_view, non_blocking=True)
+                    o = voltrix.spmm(blk, packed, hind, sh.local_rows, sh.local_nnz, feat_dev, out=out)
+                    out_host[0].copy_(o, non_blocking=True)
+
+            e2e_serial_ms = time_e2e(serial_steps)
+            del feat_dev
+        pipe = voltrix.HostStreamedSpMM(blk, packed, hind, sh.local_rows, sh.local_nnz, N, dtype=feat.dtype, input_rows=M)
 
         def streamed_steps(n):
             pipe.fork()                                         # its streams start after the `s` event on this stream
             for i in range(n):
-                pipe.submit(feat_host, out_host[i % 2])
+                pipe.submit(host_view, out_host[i % 2])
             pipe.join()                                         # this stream (and the `e` event) waits for the last D2H
 
         e2e_ms = time_e2e(streamed_steps)
-        e2e_ok = bool(torch.equal(out_host[0], out_host[1]) and torch.equal(out_host[0], out.cpu()))
+        ok = bool(torch.equal(out_host[0], out_host[1]) and torch.equal(out_host[0], out.cpu()))
+        e2e = {"value": flops / e2e_ms / 1e6, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(M * N * 2), "d2h_bytes_per_step": int(M * N * 4),
+               "result_matches_device_run": ok,
+               "api": "voltrix.HostStreamedSpMM.submit(pinned B, pinned C) every step: H2D of B (1/world row slice per rank "
+                      "+ NCCL all-gather over NVLink when world > 1), voltrix.spmm, D2H of this rank's rows of C; the three "
+                      "legs of consecutive steps overlap on three streams"}
+        if e2e_serial_ms is not None:
+            e2e["serial_ms_per_step"] = e2e_serial_ms
+            e2e["serial_value"] = flops / e2e_serial_ms / 1e6
+        del pipe, out_host
 
-    if rank != 0:
-        if world > 1:
-            dist.barrier(); dist.destroy_process_group()
-        return
+    res = {"workload": workload, "desc": desc, "M": M, "nnz": nnz, "N": N, "ms": ms, "ms_max": ms_max,
+           "per_rank_ms": per_rank_ms, "step_ms": step_ms, "tuned": tuned, "t_pre": t_pre, "t_bcast": t_bcast,
+           "t_wall": t_wall, "clocks": clocks.summary(), "parity": parity, "e2e": e2e, "sh": sh, "plan": plan,
+           "feat": feat, "state": (blk, packed, hind), "indptr": indptr, "indices": indices, "flops": flops}
+    return res
 
-    flops = 2.0 * nnz * N
-    gflops = flops / ms_max / 1e6
+
+def roofline_of(r: dict, world: int, scale: float):
+    M, N, nnz, sh, plan, ms = r["M"], r["N"], r["nnz"], r["sh"], r["plan"], r["ms"]
     peak, peak_src = measured_peak()
     abytes = alg_bytes(nnz, M, M, N, 2)
-    # roofline of the dominant kernel on rank 0: algorithmic bytes of rank 0's shard / its launch duration
+    # the dominant kernel on rank 0: algorithmic bytes of rank 0's shard / its launch duration
     abytes_local = 4 * sh.local_nnz + 4 * (sh.local_rows + 1) + M * N * 2 + sh.local_rows * N * 4
     achieved = abytes_local / (ms * 1e-3) / 1e9
     gather_bytes = (plan.total_blocks * 8 * N * 2 + 48 * plan.total_blocks + sh.local_rows * N * 4)
-    traffic, traffic_src = measured_traffic({k: v for k, v in tuned.items() if k[0] == "spmm_kernel"}, args.workload) \
-        if world == 1 and args.scale == 1.0 else (None, None)
-    # measured floors of the tensor-core kernel on THIS workload (timing-only builds, profiles/r1c_bottleneck_isolation.md):
-    # what actually bounds the launch when B is L2-resident and the compulsory-HBM fraction is structurally ~5 %
-    floors = None
-    if args.workload == "reddit" and args.scale == 1.0 and world == 1:
-        floors = {"l2_slices_to_sm_gather_ms": 1.48, "tcgen05_mma_issue_ms": 1.65, "shared_memory_port_ms": 1.64,
-                  "frac_of_binding_floor": 1.65 / ms, "source": "profiles/r1c_bottleneck_isolation.md"}
-    launches_per_step = 1 + (1 if plan.num_sparse_rows else 0) + (1 if plan.num_fixups else 0)
-    line = {
-        "metric": METRIC if N == 128 else METRIC.replace("N=128", f"N={N}"),
-        "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
-        "data": "synthetic",
-        "config": {"workload": desc, "M": M, "nnz": nnz, "N": N, "l2": "flushed (256 MB write) before every timed step",
-                   "sharding": f"{world} nnz-balanced window-aligned row ranges" if world > 1 else "none",
-                   "tuned": {str(k): v for k, v in tuned.items() if k[0] == "spmm_kernel"},
-                   "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "alg_bytes_per_launch": abytes_local,
-                     "alg_bytes_whole_job": abytes,
-                     "gather_bytes_per_launch": gather_bytes, "gather_gbs": gather_bytes / (ms * 1e-3) / 1e9,
-                     "kernel_floors": floors,
-                     "note": (f"B ({M * N * 2 / 1e6:.1f} MB fp16) is L2-resident: the kernel is bound by the L2->SM gather "
-                              "stream (gather_bytes), not by compulsory HBM bytes -- see DESIGN.md section 4.5")
-                     if M * N * 2 < 100e6 else
-                             (f"B ({M * N * 2 / 1e9:.2f} GB fp16) does not fit the 126 MB L2: the row gather "
-                              "(gather_bytes, minus L2 hits on hub rows) is what HBM actually serves -- DESIGN.md 4.5")},
-        "e2e": {"value": None, "unit": "GFLOP/s", "skipped": e2e_skipped, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-        if e2e_skipped else
-               {"value": flops / e2e_ms / 1e6, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "skipped": e2e_skipped,
-                "serial_ms_per_step": e2e_serial_ms, "serial_value": flops / e2e_serial_ms / 1e6,
-                "result_matches_device_run": e2e_ok,
-                "api": "voltrix.HostStreamedSpMM.submit(pinned feat, pinned C): H2D of B, voltrix.spmm, D2H of C "
-                       "every step; the three legs of consecutive steps overlap on three streams"},
-        "gpu_launches": launches_per_step * args.steps,
-        "clocks": clocks.summary(),
-        "preprocess_ms": t_pre * 1e3, "broadcast_ms": t_bcast * 1e3,
-        "step_ms_min_med_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],
-    }
-    if world == 1 and not args.no_baselines:
-        try:
-            line["baselines"] = gpu_baselines(indptr, indices, M, N, feat)
-            line["baselines"].update(ref_kernel_baseline(blk, packed, hind, M, nnz, N, feat))
-        except Exception as ex:
-            line["baselines"] = {"error": str(ex)[:200]}
-    if world == 1:
-        try:
-            ip_h, ix_h = indptr.cpu().numpy(), indices.cpu().numpy()
-            line["cpu_baseline"] = cpu_baseline(ip_h, ix_h, M, N)
-            if not args.no_baselines:
-                line["cpu_baseline"]["others"] = extra_cpu_baselines(ip_h, ix_h, M, N)
-                try:
-                    line["cpu_baseline"]["reference_preprocess"] = reference_preprocess_baseline(ip_h, ix_h, t_pre * 1e3)
-                except Exception as ex:
-                    line["cpu_baseline"]["reference_preprocess"] = {"error": str(ex)[:160]}
-        except Exception as ex:
-            line["cpu_baseline"] = {"error": str(ex)[:200]}
-    emit(line)
+    traffic, traffic_src = measured_traffic(r["tuned"], r["workload"]) if world == 1 and scale == 1.0 else (None, None)
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "alg_bytes_per_launch": abytes_local, "alg_bytes_whole_job": abytes,
+            "gather_bytes_per_launch": gather_bytes, "gather_gbs": gather_bytes / (ms * 1e-3) / 1e9,
+            "kernel_floors": committed_floors(r["workload"], scale, world, ms),
+            "note": (f"B ({M * N * 2 / 1e6:.1f} MB fp16) is L2-resident: the kernel is bound by the L2->SM gather "
+                     "stream (gather_bytes), not by compulsory HBM bytes -- see DESIGN.md section 4.5")
+            if M * N * 2 < 100e6 else
+                    (f"B ({M * N * 2 / 1e9:.2f} GB fp16) does not fit the 126 MB L2: the row gather "
+                     "(gather_bytes, minus L2 hits on hub rows) is what HBM actually serves -- DESIGN.md 4.5")}
+
+
+def run_product_arm(args):
+    import faulthandler
+    import torch.distributed as dist
+    # hang diagnosis: dump every thread's Python stack to stderr if the bench is still running after this long
+    faulthandler.dump_traceback_later(int(os.environ.get("VX_BENCH_STACK_DUMP_S", "1500")), repeat=False, exit=False)
+    t_start = time.perf_counter()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (product arm) needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.barrier(); dist.destroy_process_group()
+        import datetime
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # a rank that stops making progress fails the collective after VX_BENCH_NCCL_TIMEOUT_S instead of 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(
+            seconds=int(os.environ.get("VX_BENCH_NCCL_TIMEOUT_S", "600"))))
+
+    r = measure(args.workload, args, world, rank, dev, headline=True, steps=args.steps, warmup=args.warmup)
+    M, N, nnz, sh, plan, ms_max, ms = r["M"], r["N"], r["nnz"], r["sh"], r["plan"], r["ms_max"], r["ms"]
+    flops = r["flops"]
+    launches_per_step = 1 + (1 if plan.num_sparse_rows else 0) + (1 if plan.num_fixups else 0)   # kernels (+ one 4-byte memset)
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC if N == 128 else METRIC.replace("N=128", f"N={N}"),
+            "value": flops / ms_max / 1e6, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": workload_config(r["desc"], M, nnz, N),
+            "details": {"sharding": f"{world} cost-balanced window-aligned row ranges" if world > 1 else "none",
+                        "tuned": r["tuned"], "wall_ms_per_step_incl_flush": r["t_wall"] * 1e3 / args.steps,
+                        "per_rank_ms": r["per_rank_ms"], "scheduler": "atomic-ticket claiming of LPT-sorted units, "
+                        "feature-tile-major"},
+            "roofline": roofline_of(r, world, args.scale),
+            "parity": r["parity"],
+            "e2e": r["e2e"],
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": r["clocks"],
+            "preprocess_ms": r["t_pre"] * 1e3 if r["t_pre"] else None, "broadcast_ms": r["t_bcast"] * 1e3,
+            "step_ms_min_med_max": [float(np.min(r["step_ms"])), float(np.median(r["step_ms"])), float(np.max(r["step_ms"]))],
+        }
+        if world == 1 and not args.no_baselines:
+            try:
+                blk, packed, hind = r["state"]
+                line["baselines"] = gpu_baselines(r["indptr"], r["indices"], M, N, r["feat"])
+                line["baselines"].update(ref_kernel_baseline(blk, packed, hind, M, nnz, N, r["feat"]))
+            except Exception as ex:
+                line["baselines"] = {"error": str(ex)[:200]}
+        if world == 1:
+            try:
+                ip_h, ix_h = r["indptr"].cpu().numpy(), r["indices"].cpu().numpy()
+                line["cpu_baseline"] = cpu_baseline(ip_h, ix_h, M, N)
+                if not args.no_baselines:
+                    line["cpu_baseline"]["others"] = extra_cpu_baselines(ip_h, ix_h, M, N)
+                    try:
+                        line["cpu_baseline"]["reference_preprocess"] = reference_preprocess_baseline(
+                            ip_h, ix_h, r["t_pre"] * 1e3 if r["t_pre"] else None)
+                    except Exception as ex:
+                        line["cpu_baseline"]["reference_preprocess"] = {"error": str(ex)[:160]}
+                del ip_h, ix_h
+            except Exception as ex:
+                line["cpu_baseline"] = {"error": str(ex)[:200]}
+    del r
+    torch.cuda.empty_cache()
+
+    # --- the other north_star configurations, device-timed at this N (C4 products-shaped N=256; C5 R-MAT 2^25 rows) ---
+    extras = [w for w in args.extra.split(",") if w and w != args.workload] if args.scale == 1.0 else []
+    # An extra must never cost the headline: if one of them wedges (a rank lost inside a collective), every rank leaves
+    # at the deadline and rank 0 prints the line with what it has.
+    emitted = threading.Lock()
+
+    def bail_out():
+        if rank == 0 and emitted.acquire(blocking=False):
+            line.setdefault("extra", {})["watchdog"] = f"extras cut off after {args.extra_budget_s + 240:.0f} s"
+            emit(line)
+        os._exit(0)
+
+    watchdog = threading.Timer(args.extra_budget_s + 240, bail_out)
+    watchdog.daemon = True
+    if extras:
+        watchdog.start()
+    for w in extras:
+        spent = torch.tensor([time.perf_counter() - t_start], device=dev)
+        if world > 1:
+            dist.all_reduce(spent, op=dist.ReduceOp.MAX)          # rank-invariant decision
+        if float(spent.item()) > args.extra_budget_s:
+            if rank == 0:
+                line.setdefault("extra", {})[w] = {"skipped": f"time budget ({args.extra_budget_s:.0f} s) spent"}
+            continue
+        try:
+            x = measure(w, args, world, rank, dev, headline=False, steps=min(args.steps, 10), warmup=3)
+            if rank == 0:
+                rf = roofline_of(x, world, args.scale)
+                line.setdefault("extra", {})[w] = {
+                    "config": workload_config(x["desc"], x["M"], x["nnz"], x["N"]),
+                    "value": x["flops"] / x["ms_max"] / 1e6, "unit": "GFLOP/s", "ms_per_step": x["ms_max"],
+                    "per_rank_ms": x["per_rank_ms"], "tuned": x["tuned"], "parity": x["parity"],
+                    "roofline": {k: rf[k] for k in ("achieved", "peak", "frac", "traffic", "traffic_source",
+                                                    "alg_bytes_whole_job", "gather_gbs")},
+                    "e2e": x["e2e"], "clocks": x["clocks"],
+                    "shard_rows": [b - a for a, b in x["sh"].ranges]}
+            del x
+        except Exception as ex:   # an extra must never cost the headline line
+            log(f"[rank {rank}] extra workload {w} failed: {ex!r}")
+            if rank == 0:
+                line.setdefault("extra", {})[w] = {"error": repr(ex)[:300]}
+            if world > 1:
+                break             # ranks may have diverged inside a collective: stop issuing more
+        torch.cuda.empty_cache()
+    faulthandler.cancel_dump_traceback_later()
+    watchdog.cancel()
+    if rank == 0 and emitted.acquire(blocking=False):
+        emit(line)
+    if world > 1:
+        try:
+            dist.barrier(); dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 def emit(line: dict):
@@ -558,6 +716,11 @@ def main():
     ap.add_argument("--workload", default="reddit", choices=["reddit", "products", "rmat25", "c1"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debug)")
     ap.add_argument("--no-baselines", action="store_true")
+    ap.add_argument("--extra", default=os.environ.get("VX_BENCH_EXTRA", "products,rmat25"),
+                    help="comma-separated workloads measured after the headline one and reported under `extra`")
+    ap.add_argument("--extra-budget-s", type=float, default=float(os.environ.get("VX_BENCH_EXTRA_BUDGET_S", "420")),
+                    help="no further extra workload is started once the run is this old")
+    ap.add_argument("--e2e-extras", action="store_true", help="also run the host-buffer leg on the extra workloads")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

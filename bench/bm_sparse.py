@@ -1,32 +1,27 @@
-"""cuSPARSE baseline (reference: bench/bm_sparse.py:1-52): torch.sparse_csr @ dense, 10 warm + 100 timed
-iterations, CUDA events; prints `[cuSPARSE] Elapsed time: x ms`."""
+"""cuSPARSE baseline beside bench/bm_voltrix.py: `torch.sparse_csr @ dense` on the files graph_gen.py wrote into the CWD.
+Prints the three lines bench_all.py and the reference's README read: nnz, the allclose verdict against output_base.csv
+(atol 1e-1, the reference's bar, bench/bm_sparse.py:50) and `[cuSPARSE] Elapsed time: x ms` (10 warm-up + 100 timed
+back-to-back calls between CUDA events -- voltrix.utils.GPU_bench without a kernel name)."""
+import os
+import sys
+
 import numpy as np
 import torch
 
-indices = torch.tensor(np.loadtxt("indices.csv", delimiter=",", dtype=np.int32), dtype=torch.int32).cuda()
-offsets = torch.tensor(np.loadtxt("indptr.csv", delimiter=",", dtype=np.int32), dtype=torch.int32).cuda()
-N = offsets.numel() - 1
-csr = torch.sparse_csr_tensor(offsets, indices, values=torch.ones_like(indices).float(), size=(N, N)).cuda()
-print(indices.numel())
-weight = torch.tensor(np.fromfile("feat.csv", dtype=np.float32)).cuda().view(N, -1)
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "voltrix-spmm_b200")))
+from voltrix.utils import GPU_bench  # noqa: E402
 
 
-def f():
-    return csr @ weight
+def load_csv_int32(name):
+    return torch.from_numpy(np.loadtxt(name, delimiter=",", dtype=np.int32)).cuda()
 
 
-iters = 100
-for _ in range(10):
-    o = f()
-torch.cuda.synchronize()
-start_event = torch.cuda.Event(enable_timing=True)
-end_event = torch.cuda.Event(enable_timing=True)
-start_event.record()
-for _ in range(iters):
-    o = f()
-end_event.record()
-torch.cuda.synchronize()
-o = f()
-o_base = np.fromfile("output_base.csv", dtype=np.float32).reshape(*list(o.shape))
-print(np.allclose(o.detach().cpu().numpy(), o_base, atol=1e-1))
-print(f"[cuSPARSE] Elapsed time: {start_event.elapsed_time(end_event) / iters:.4f} ms")
+col, rowptr = load_csv_int32("indices.csv"), load_csv_int32("indptr.csv")
+rows = rowptr.numel() - 1
+dense = torch.from_numpy(np.fromfile("feat.csv", dtype=np.float32)).cuda().view(rows, -1)
+adjacency = torch.sparse_csr_tensor(rowptr, col, torch.ones(col.numel(), device="cuda"), size=(rows, rows))
+print(col.numel())
+ms = GPU_bench(lambda: adjacency @ dense, iters=100, warmup=10)
+expected = np.fromfile("output_base.csv", dtype=np.float32).reshape(rows, -1)
+print(np.allclose((adjacency @ dense).cpu().numpy(), expected, atol=1e-1))
+print(f"[cuSPARSE] Elapsed time: {ms:.4f} ms")

@@ -110,6 +110,10 @@ typedef struct {
   const float *row_scale;      /* [num_nodes] */
   const float *bias;           /* [embedding_dim] */
   int32_t relu;
+  /* ABI v5: 4 bytes of device memory the tensor-core kernel claims its work units from (atomic ticket: persistent CTAs
+   * take the next unit of the LPT list when they finish one).  One per stream that may have a launch in flight; zeroed by
+   * vx_spmm on `stream`.  NULL = static striding over the list. */
+  int32_t *ticket;
 } vx_plan_t;
 
 /* `stages` (models 0 and 3) = K-steps of 16 gathered rows kept in flight; it selects a compiled variant, each with its

@@ -79,6 +79,26 @@ def _worker(rank, world, port, q):
         full = sh.all_gather(c_local)
         want = torch.from_numpy(oracle.c().spmm_csr(A.indptr.astype(np.int32), A.indices.astype(np.int32), B.numpy()))
         ok = torch.equal(full, want) and sh.ranges[0][0] == 0 and sh.ranges[-1][1] == M
+        # reusing a caller-owned result buffer gives the same rows
+        again = sh.all_gather(c_local, out=torch.full((M, N), float("nan")))
+        ok = ok and torch.equal(again, want)
+        # per-step operand exchange: every rank owns only ITS row slice of the host operand (the rest is poisoned);
+        # upload + all-gather must rebuild the whole operand on every rank, padding rows excluded
+        from voltrix.distributed import operand_slices, upload_slice_and_all_gather
+        chunk, slices = operand_slices(M, world)
+        lo, hi = slices[rank]
+        mine_only = torch.full((M, N), float("nan"))
+        mine_only[lo:hi] = B[lo:hi]
+        buf = torch.full((chunk * world, N), float("nan"))
+        got = upload_slice_and_all_gather(buf, mine_only, rank, world)
+        ok = ok and got.shape == (M, N) and torch.equal(got, B)
+        # the local_csr route (no rank holds the whole matrix) cuts the same shards
+        def local_csr(r0, r1):
+            lo_e, hi_e = int(indptr[r0]), int(indptr[r1])
+            return (indptr[r0:r1 + 1] - lo_e).to(torch.int32), indices[lo_e:hi_e]
+        sh2 = ShardedSpMM(None, None, M, weights=(indptr[1:] - indptr[:-1]) + 12, local_preprocess=local_preprocess,
+                          local_spmm=local_spmm, local_csr=local_csr)
+        ok = ok and sh2.ranges == sh.ranges and torch.equal(sh2.spmm(B), c_local)
         q.put((rank, bool(ok), sh.ranges))
     finally:
         dist.destroy_process_group()
@@ -120,3 +140,14 @@ def test_row_cost_balances_skewed_row_counts():
     rng = partition_rows(deg + ROW_COST, 4)
     assert rng[0][0] == 0 and rng[-1][1] == deg.numel() and all(a % 16 == 0 for a, _ in rng)
     assert all(rng[k][1] == rng[k + 1][0] for k in range(3))
+
+
+def test_operand_slices_cover_rows_once():
+    from voltrix.distributed import operand_slices
+    for rows, world in ((1000, 2), (1000, 8), (7, 8), (232_965, 8), (16, 1), (0, 4)):
+        chunk, slices = operand_slices(rows, world)
+        assert len(slices) == world and chunk * world >= rows
+        assert slices[0][0] == 0 and slices[-1][1] == rows
+        assert all(a <= b and b - a <= chunk for a, b in slices)
+        assert all(slices[k][1] == slices[k + 1][0] for k in range(world - 1))
+        assert all(a == min(k * chunk, rows) for k, (a, _) in enumerate(slices))   # slice k starts at rank k's all-gather slot

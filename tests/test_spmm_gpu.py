@@ -16,25 +16,30 @@ DTYPES = [torch.float32, torch.float16, torch.bfloat16]
 TOL = {torch.float32: 2e-5, torch.float16: 1e-4, torch.bfloat16: 1e-4}
 
 
+# every tensor-core variant of the autotune space (jit_kernels/spmm.py::SPACE_HALF: 36/12, 42/14 -- the usual winner --,
+# 32/16, 40/24 = the two-producer-group geometry) plus the small test-only ones: (model, K-steps in flight[, producer warps])
+TC_VARIANTS = [(0, 16), (0, 32), (0, 36), (0, 42), (0, 32, 16), (0, 40)]
+
+
 def _scaled_err(got, want):
     return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-9))
 
 
 def _run_all_models(voltrix, blk, packed, hind, M, E, feat):
     out = {}
-    models = [(1, 32), (2, 32), (3, 24)] if feat.dtype == torch.float32 else [(0, 16), (0, 32), (0, 36), (1, 32), (2, 32)]
-    for model, stages in models:
+    models = [(1, 32), (2, 32), (3, 24)] if feat.dtype == torch.float32 else TC_VARIANTS + [(1, 32), (2, 32)]
+    for model, stages, *rest in models:
         o = torch.full((M, feat.shape[1]), float("nan"), device="cuda")
         try:
             voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=E, embedding_dim=feat.shape[1], input=feat,
-                                output=o, model=model, stages=stages)
+                                output=o, model=model, stages=stages, npw=rest[0] if rest else None)
         except RuntimeError as e:
             if "invalid argument" in str(e):   # model 1 without CSR (duplicates in the input)
                 continue
             if model == 3 and "unsupported" in str(e) and feat.shape[1] % 8 != 0:   # TMA stride rule: N % 8 == 0
                 continue
             raise
-        out[(model, stages)] = o.cpu().numpy()
+        out[(model, stages, *rest)] = o.cpu().numpy()
     return out
 
 
@@ -54,7 +59,7 @@ def test_every_path_matches_oracle(golden_cases, name, dtype, N):
     outs = _run_all_models(voltrix, blk, packed, hind, M, E, feat)
     assert outs, "no kernel path ran"
     if not packed._vx_plan.has_duplicates:
-        assert any(m == 1 for m, _ in outs), "CSR path must run on coalesced input"
+        assert any(k[0] == 1 for k in outs), "CSR path must run on coalesced input"
     for key, got in outs.items():
         assert np.isfinite(got).all(), f"{key}: unwritten output rows"
         assert _scaled_err(got, want) <= TOL[dtype], f"model/stages {key}"
@@ -63,8 +68,9 @@ def test_every_path_matches_oracle(golden_cases, name, dtype, N):
     assert _scaled_err(got, want) <= TOL[dtype]
 
 
+@pytest.mark.parametrize("variant", [(16, None), (36, None), (42, None), (32, 16), (40, None)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-def test_sparse_window_routing_and_k_split(dtype):
+def test_sparse_window_routing_and_k_split(dtype, variant):
     """A matrix with one hub window (split along K), many ordinary windows and very sparse windows
     (routed to the CUDA-core row path): all three mechanisms in one SpMM, result equals the oracle."""
     import voltrix
@@ -91,17 +97,19 @@ def test_sparse_window_routing_and_k_split(dtype):
     feat = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32)).cuda().to(dtype)
     p1, pk, hi = oracle.c().csr_to_tiles(indptr, indices)
     want = oracle.c().spmm_tiles(p1, pk, hi, M, feat.float().cpu().numpy())
+    stages, npw = variant
     o = torch.full((M, N), float("nan"), device="cuda")
     voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=indices.size, embedding_dim=N, input=feat, output=o,
-                        model=0, stages=16)
+                        model=0, stages=stages, npw=npw)
     got = o.cpu().numpy()
     assert np.isfinite(got).all()
     assert _scaled_err(got, want) <= 1e-4
-    # run-to-run determinism (fixed-order fix-up, no float atomics)
-    o2 = torch.empty_like(o)
-    voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=indices.size, embedding_dim=N, input=feat, output=o2,
-                        model=0, stages=16)
-    assert torch.equal(o, o2)
+    # run-to-run determinism (fixed-order fix-up, no float atomics; which CTA claims which unit does not matter)
+    for _ in range(3):
+        o2 = torch.empty_like(o)
+        voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=indices.size, embedding_dim=N, input=feat, output=o2,
+                            model=0, stages=stages, npw=npw)
+        assert torch.equal(o, o2)
 
 
 def test_reference_test_generator_difference_rate():
@@ -268,7 +276,7 @@ def test_fused_epilogue_every_model(dtype):
     blk, packed, hind = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
     plan = packed._vx_plan
     assert plan.num_fixups >= 1 and plan.num_sparse_rows > 0
-    models = [(1, 32), (2, 32), (3, 24)] if dtype == torch.float32 else [(0, 16), (0, 36), (1, 32), (2, 32)]
+    models = [(1, 32), (2, 32), (3, 24)] if dtype == torch.float32 else [(0, 16), (0, 36), (0, 42), (0, 40), (1, 32), (2, 32)]
     for model, stages in models:
         plain = torch.empty(M, N, device="cuda")
         voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=indices.size, embedding_dim=N, input=feat,
@@ -319,7 +327,7 @@ def test_c_abi_plan_with_epilogue():
                     ("num_fixups", ctypes.c_int32), ("scratch", ctypes.c_void_p), ("csr_indptr", ctypes.c_void_p),
                     ("csr_indices", ctypes.c_void_p), ("sparse_rows", ctypes.c_void_p), ("num_sparse_rows", ctypes.c_int32),
                     ("input_rows", ctypes.c_int64), ("split_ws", ctypes.c_void_p), ("row_scale", ctypes.c_void_p),
-                    ("bias", ctypes.c_void_p), ("relu", ctypes.c_int32)]
+                    ("bias", ctypes.c_void_p), ("relu", ctypes.c_int32), ("ticket", ctypes.c_void_p)]
 
     indptr, indices, M = _epilogue_case()
     N = 128
@@ -331,7 +339,7 @@ def test_c_abi_plan_with_epilogue():
     scratch = p.scratch(N)
     plan = Plan(p.items.data_ptr(), p.num_items, p.fixups.data_ptr(), p.num_fixups, scratch.data_ptr() if scratch is not None else None,
                 p.csr_indptr.data_ptr(), p.csr_indices.data_ptr(), p.sparse_rows.data_ptr(), p.num_sparse_rows, M, None,
-                scale.data_ptr(), bias.data_ptr(), 1)
+                scale.data_ptr(), bias.data_ptr(), 1, None)
     vp, i32 = ctypes.c_void_p, ctypes.c_int32
     lib.vx_spmm.restype = ctypes.c_int
     lib.vx_spmm.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, vp, i32, i32, ctypes.POINTER(Plan), vp]
@@ -343,6 +351,16 @@ def test_c_abi_plan_with_epilogue():
     want = torch.relu(voltrix.spmm(blk, packed, hind, M, indices.size, feat) * scale[:, None] + bias[None, :])
     assert torch.isfinite(out).all()
     assert (out - want).abs().max().item() / want.abs().max().item() <= 1e-6
+    # ABI v5: with a ticket counter the persistent CTAs claim their units dynamically; same bits out
+    ticket = torch.full((4,), 12345, dtype=torch.int32, device="cuda")   # vx_spmm zeroes it on the stream
+    plan.ticket = ticket.data_ptr()
+    out2 = torch.full((M, N), float("nan"), device="cuda")
+    rc = lib.vx_spmm(blk.data_ptr(), packed.data_ptr(), hind.data_ptr(), M, indices.size, N, feat.data_ptr(), 1,
+                     out2.data_ptr(), 0, 42, ctypes.byref(plan), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
+    assert int(ticket[0]) >= plan.num_items    # every unit beyond the first grid-full was claimed through the counter
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])

@@ -44,7 +44,7 @@ static int csr_weighted_dispatch(const int32_t *indptr, const int32_t *indices, 
 
 extern "C" {
 
-int vx_abi_version(void) { return 4; }
+int vx_abi_version(void) { return 5; }
 
 size_t vx_preprocess_workspace_bytes(int64_t num_edges, int32_t num_nodes) {
   return preprocess_workspace_bytes(num_edges, num_nodes);
@@ -131,6 +131,7 @@ int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32
     p.epilogue.row_scale = plan->row_scale;
     p.epilogue.bias = plan->bias;
     p.epilogue.relu = plan->relu;
+    p.ticket = plan->ticket;
   }
   cudaStream_t s = (cudaStream_t)stream;
   switch (input_dtype) {

@@ -2,13 +2,13 @@
 //
 // Two kernels, both fp32-accumulating and exact for fp32 input (no TF32 rounding):
 //
-//  * vx_csr_rows_kernel   -- one warp per output row, straight from CSR.  Lane groups of
+//  * vx_spmm_csr_rows_kernel   -- one warp per output row, straight from CSR.  Lane groups of
 //    LANES threads cover one B-row slice with 16-byte loads; 32/LANES groups walk the row's
 //    non-zeros in parallel, 4 deep, and are shuffle-reduced at the end.  This is the path for
 //    windows too sparse to fill an MMA tile (north_star subsystem 3): it gathers exactly
 //    nnz(row) B rows, whereas a 16x8 TC block always gathers 8.
 //
-//  * vx_tile_rows_kernel  -- one warp per output row, from the reference tile format
+//  * vx_spmm_tile_rows_kernel  -- one warp per output row, from the reference tile format
 //    (blk_offsets, hspa_packed, hind) only.  Used when a caller hands us nothing but the
 //    reference triple (kernel-level API) and the tcgen05 path does not apply (N % 64 != 0).
 //
@@ -17,6 +17,8 @@
 // C[row, :] = sum over distinct columns c of row of B[c, :], fp32 accumulation.
 #ifndef VOLTRIX_B200_SPMM_CUDA_CORE_CUH_
 #define VOLTRIX_B200_SPMM_CUDA_CORE_CUH_
+
+#include <type_traits>
 
 #include "voltrix/common.cuh"
 
@@ -77,16 +79,46 @@ __device__ __forceinline__ uint4 vx_ldg16(const void *p) {
   return __ldg(reinterpret_cast<const uint4 *>(p));
 }
 
+// Row-slice access policies of the kernels below.  VecAccess: 16-byte loads of B, float4 stores of C (needs
+// N % (16 / sizeof(T)) == 0 and 16-byte aligned B / C).  ScalarAccess: one element per lane -- any N, any alignment;
+// the launchers fall back to it when the vector rule does not hold (N = 100, N = 1, odd row strides ...).
+template <typename T>
+struct VecAccess {
+  static constexpr int N = Vec16<T>::N;
+  using Reg = uint4;
+  __device__ static Reg load(const T *p) { return vx_ldg16(p); }
+  __device__ static void add(float (&acc)[N], const Reg &v) { Vec16<T>::add(acc, v); }
+  __device__ static void fma(float (&acc)[N], const Reg &v, float w) { Vec16<T>::fma(acc, v, w); }
+  __device__ static void store(float *dst, const float (&acc)[N]) {
+    float4 *d = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) d[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+  }
+};
+template <typename T>
+struct ScalarAccess {
+  static constexpr int N = 1;
+  using Reg = float;
+  __device__ static Reg load(const T *p) {
+    if constexpr (sizeof(T) == 4) return __ldg(reinterpret_cast<const float *>(p));
+    else if constexpr (std::is_same<T, __half>::value) return __half2float(__ldg(p));
+    else return __uint_as_float(uint32_t(__ldg(reinterpret_cast<const unsigned short *>(p))) << 16);
+  }
+  __device__ static void add(float (&acc)[1], const Reg &v) { acc[0] += v; }
+  __device__ static void fma(float (&acc)[1], const Reg &v, float w) { acc[0] = fmaf(w, v, acc[0]); }
+  __device__ static void store(float *dst, const float (&acc)[1]) { dst[0] = acc[0]; }
+};
+
 // rows: either all rows [0, num_rows) (row_list == nullptr) or the rows named by
 // row_list[0..num_rows).  grid.x * warps_per_block >= num_rows, grid.y = feature chunks.
 // WEIGHTED: `vals[e]` multiplies the gathered row of non-zero e (general CSR values).  The
 // binary instantiation is the product path of the tile format; the weighted one serves voltrix.spmm_weighted.
-template <typename T, int LANES, bool WEIGHTED = false>
+template <typename T, int LANES, bool WEIGHTED = false, typename A = VecAccess<T>>
 __global__ void __launch_bounds__(256)
-vx_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+vx_spmm_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                    const int32_t *__restrict__ row_list, int32_t num_rows, int32_t N,
                    const T *__restrict__ B, float *__restrict__ C, Epilogue epi, const float *__restrict__ vals = nullptr) {
-  constexpr int EPL = Vec16<T>::N;            // elements per lane per load
+  constexpr int EPL = A::N;               // elements per lane per load
   constexpr int GROUPS = 32 / LANES;          // non-zeros processed in parallel by one warp
   constexpr int CHUNK = LANES * EPL;          // features covered by one pass
   const int lane = threadIdx.x & 31;
@@ -110,22 +142,22 @@ vx_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
     int32_t c0 = __ldg(indices + e), c1 = __ldg(indices + e + GROUPS);
     int32_t c2 = __ldg(indices + e + 2 * GROUPS), c3 = __ldg(indices + e + 3 * GROUPS);
     if (active) {
-      uint4 v0 = vx_ldg16(Bf + int64_t(c0) * N), v1 = vx_ldg16(Bf + int64_t(c1) * N);
-      uint4 v2 = vx_ldg16(Bf + int64_t(c2) * N), v3 = vx_ldg16(Bf + int64_t(c3) * N);
+      const typename A::Reg v0 = A::load(Bf + int64_t(c0) * N), v1 = A::load(Bf + int64_t(c1) * N);
+      const typename A::Reg v2 = A::load(Bf + int64_t(c2) * N), v3 = A::load(Bf + int64_t(c3) * N);
       if constexpr (WEIGHTED) {
-        Vec16<T>::fma(acc, v0, __ldg(vals + e)); Vec16<T>::fma(acc, v1, __ldg(vals + e + GROUPS));
-        Vec16<T>::fma(acc, v2, __ldg(vals + e + 2 * GROUPS)); Vec16<T>::fma(acc, v3, __ldg(vals + e + 3 * GROUPS));
+        A::fma(acc, v0, __ldg(vals + e)); A::fma(acc, v1, __ldg(vals + e + GROUPS));
+        A::fma(acc, v2, __ldg(vals + e + 2 * GROUPS)); A::fma(acc, v3, __ldg(vals + e + 3 * GROUPS));
       } else {
-        Vec16<T>::add(acc, v0); Vec16<T>::add(acc, v1);
-        Vec16<T>::add(acc, v2); Vec16<T>::add(acc, v3);
+        A::add(acc, v0); A::add(acc, v1);
+        A::add(acc, v2); A::add(acc, v3);
       }
     }
   }
   for (; e < end; e += GROUPS) {
     int32_t c0 = __ldg(indices + e);
     if (active) {
-      if constexpr (WEIGHTED) Vec16<T>::fma(acc, vx_ldg16(Bf + int64_t(c0) * N), __ldg(vals + e));
-      else Vec16<T>::add(acc, vx_ldg16(Bf + int64_t(c0) * N));
+      if constexpr (WEIGHTED) A::fma(acc, A::load(Bf + int64_t(c0) * N), __ldg(vals + e));
+      else A::add(acc, A::load(Bf + int64_t(c0) * N));
     }
   }
   // fixed-order tree reduction over the lane groups (deterministic)
@@ -140,9 +172,7 @@ vx_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
 #pragma unroll
       for (int i = 0; i < EPL; ++i) acc[i] = epi.apply(acc[i], sc, epi.bias_of(f0 + i));
     }
-    float4 *dst = reinterpret_cast<float4 *>(C + int64_t(row) * N + f0);
-#pragma unroll
-    for (int i = 0; i < EPL / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    A::store(C + int64_t(row) * N + f0, acc);
   }
 }
 
@@ -151,7 +181,7 @@ vx_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict
 // without a non-zero; here every group walks its own row, 4 gathers deep.
 template <typename T, int LANES, bool WEIGHTED = false>
 __global__ void __launch_bounds__(256)
-vx_csr_subwarp_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+vx_spmm_csr_subwarp_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                            const int32_t *__restrict__ row_list, int32_t num_rows, int32_t N,
                            const T *__restrict__ B, float *__restrict__ C, Epilogue epi,
                            const float *__restrict__ vals = nullptr) {
@@ -200,12 +230,12 @@ vx_csr_subwarp_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__
 // One warp per row of the tile format.  Lane l scans TC block (b0 + l) of the row's window for
 // its 8-bit column mask, then the warp walks the set bits together: every step all 32 lanes load
 // one 512-byte slice of one B row.
-template <typename T>
+template <typename T, typename A = VecAccess<T>>
 __global__ void __launch_bounds__(256)
-vx_tile_rows_kernel(const int32_t *__restrict__ blk_offsets, const uint32_t *__restrict__ packed,
+vx_spmm_tile_rows_kernel(const int32_t *__restrict__ blk_offsets, const uint32_t *__restrict__ packed,
                     const int32_t *__restrict__ hind, int32_t num_nodes, int32_t N,
                     const T *__restrict__ B, float *__restrict__ C, Epilogue epi) {
-  constexpr int EPL = Vec16<T>::N;
+  constexpr int EPL = A::N;
   constexpr int CHUNK = 32 * EPL;
   const int lane = threadIdx.x & 31;
   const int32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -238,7 +268,7 @@ vx_tile_rows_kernel(const int32_t *__restrict__ blk_offsets, const uint32_t *__r
         int c = __ffs(m) - 1;
         m &= m - 1;
         int32_t col = __ldg(cols + c);
-        if (active) Vec16<T>::add(acc, vx_ldg16(Bf + int64_t(col) * N));
+        if (active) A::add(acc, A::load(Bf + int64_t(col) * N));
       }
     }
   }
@@ -248,15 +278,18 @@ vx_tile_rows_kernel(const int32_t *__restrict__ blk_offsets, const uint32_t *__r
 #pragma unroll
       for (int i = 0; i < EPL; ++i) acc[i] = epi.apply(acc[i], sc, epi.bias_of(f0 + i));
     }
-    float4 *dst = reinterpret_cast<float4 *>(C + int64_t(row) * N + f0);
-#pragma unroll
-    for (int i = 0; i < EPL / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    A::store(C + int64_t(row) * N + f0, acc);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+// 16-byte row slices need N to be a multiple of the vector width and both operands 16-byte aligned.
+inline bool vec_access_ok(int32_t N, int epl, const void *B, const void *C) {
+  return N % epl == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+}
+
 // mean_degree: non-zeros per row of the rows being computed (< 0 = unknown).  Rows with fewer non-zeros than a warp
 // has lane groups go to the group-per-row kernel; the choice depends only on (mean_degree, N), never on timing.
 template <typename T>
@@ -265,23 +298,29 @@ inline int launch_csr_rows(const int32_t *indptr, const int32_t *indices, const 
                            const Epilogue &epi = Epilogue()) {
   constexpr int EPL = Vec16<T>::N;
   if (num_rows <= 0) return VX_OK;
-  if (N <= 0 || N % EPL != 0) return VX_ERR_UNSUPPORTED;
-  int lanes_needed = N / EPL;  // 16-byte loads per row
+  if (N <= 0) return VX_ERR_INVALID_ARG;
   dim3 block(256);
+  if (!vec_access_ok(N, EPL, B, C)) {   // any N, any alignment: one element per lane
+    vx_spmm_csr_rows_kernel<T, 32, false, ScalarAccess<T>><<<dim3(ceil_div(num_rows, 8), ceil_div(N, 32)), block, 0, stream>>>(
+        indptr, indices, row_list, num_rows, N, B, C, epi);
+    VX_LAUNCH_CHECK();
+    return VX_OK;
+  }
+  int lanes_needed = N / EPL;  // 16-byte loads per row
   const int lanes = lanes_needed <= 4 ? 4 : lanes_needed <= 8 ? 8 : lanes_needed <= 16 ? 16 : 32;
   if (lanes < 32 && mean_degree >= 0.f && mean_degree < 4.f * float(32 / lanes)) {
     dim3 g(unsigned(ceil_div<int64_t>(int64_t(num_rows) * lanes, 256)), ceil_div(N, lanes * EPL));
-    if (lanes == 4)      vx_csr_subwarp_rows_kernel<T, 4><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
-    else if (lanes == 8) vx_csr_subwarp_rows_kernel<T, 8><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
-    else                 vx_csr_subwarp_rows_kernel<T, 16><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+    if (lanes == 4)      vx_spmm_csr_subwarp_rows_kernel<T, 4><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+    else if (lanes == 8) vx_spmm_csr_subwarp_rows_kernel<T, 8><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+    else                 vx_spmm_csr_subwarp_rows_kernel<T, 16><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
     VX_LAUNCH_CHECK();
     return VX_OK;
   }
   auto grid = [&](int l) { return dim3(ceil_div(num_rows, 8), ceil_div(N, l * EPL)); };
-  if (lanes == 4)       vx_csr_rows_kernel<T, 4><<<grid(4), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
-  else if (lanes == 8)  vx_csr_rows_kernel<T, 8><<<grid(8), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
-  else if (lanes == 16) vx_csr_rows_kernel<T, 16><<<grid(16), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
-  else                  vx_csr_rows_kernel<T, 32><<<grid(32), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+  if (lanes == 4)       vx_spmm_csr_rows_kernel<T, 4><<<grid(4), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+  else if (lanes == 8)  vx_spmm_csr_rows_kernel<T, 8><<<grid(8), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+  else if (lanes == 16) vx_spmm_csr_rows_kernel<T, 16><<<grid(16), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+  else                  vx_spmm_csr_rows_kernel<T, 32><<<grid(32), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
   VX_LAUNCH_CHECK();
   return VX_OK;
 }
@@ -293,25 +332,30 @@ inline int launch_csr_rows_weighted(const int32_t *indptr, const int32_t *indice
                                     const Epilogue &epi = Epilogue()) {
   constexpr int EPL = Vec16<T>::N;
   if (num_rows <= 0) return VX_OK;
-  if (vals == nullptr) return VX_ERR_INVALID_ARG;
-  if (N <= 0 || N % EPL != 0) return VX_ERR_UNSUPPORTED;
+  if (vals == nullptr || N <= 0) return VX_ERR_INVALID_ARG;
+  if (!vec_access_ok(N, EPL, B, C)) {
+    vx_spmm_csr_rows_kernel<T, 32, true, ScalarAccess<T>><<<dim3(ceil_div(num_rows, 8), ceil_div(N, 32)), dim3(256), 0, stream>>>(
+        indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+    VX_LAUNCH_CHECK();
+    return VX_OK;
+  }
   const int lanes_needed = N / EPL;
   const int lanes = lanes_needed <= 4 ? 4 : lanes_needed <= 8 ? 8 : lanes_needed <= 16 ? 16 : 32;
   const float mean_degree = float(num_edges) / float(num_rows);
   dim3 block(256);
   if (lanes < 32 && mean_degree < 4.f * float(32 / lanes)) {
     dim3 g(unsigned(ceil_div<int64_t>(int64_t(num_rows) * lanes, 256)), ceil_div(N, lanes * EPL));
-    if (lanes == 4)      vx_csr_subwarp_rows_kernel<T, 4, true><<<g, block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
-    else if (lanes == 8) vx_csr_subwarp_rows_kernel<T, 8, true><<<g, block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
-    else                 vx_csr_subwarp_rows_kernel<T, 16, true><<<g, block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+    if (lanes == 4)      vx_spmm_csr_subwarp_rows_kernel<T, 4, true><<<g, block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+    else if (lanes == 8) vx_spmm_csr_subwarp_rows_kernel<T, 8, true><<<g, block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+    else                 vx_spmm_csr_subwarp_rows_kernel<T, 16, true><<<g, block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
     VX_LAUNCH_CHECK();
     return VX_OK;
   }
   auto grid = [&](int l) { return dim3(ceil_div(num_rows, 8), ceil_div(N, l * EPL)); };
-  if (lanes == 4)       vx_csr_rows_kernel<T, 4, true><<<grid(4), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
-  else if (lanes == 8)  vx_csr_rows_kernel<T, 8, true><<<grid(8), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
-  else if (lanes == 16) vx_csr_rows_kernel<T, 16, true><<<grid(16), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
-  else                  vx_csr_rows_kernel<T, 32, true><<<grid(32), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+  if (lanes == 4)       vx_spmm_csr_rows_kernel<T, 4, true><<<grid(4), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+  else if (lanes == 8)  vx_spmm_csr_rows_kernel<T, 8, true><<<grid(8), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+  else if (lanes == 16) vx_spmm_csr_rows_kernel<T, 16, true><<<grid(16), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+  else                  vx_spmm_csr_rows_kernel<T, 32, true><<<grid(32), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
   VX_LAUNCH_CHECK();
   return VX_OK;
 }
@@ -322,9 +366,13 @@ inline int launch_tile_rows(const int32_t *blk_offsets, const uint32_t *packed, 
                             const Epilogue &epi = Epilogue()) {
   constexpr int EPL = Vec16<T>::N;
   if (num_nodes <= 0) return VX_OK;
-  if (N <= 0 || N % EPL != 0) return VX_ERR_UNSUPPORTED;
+  if (N <= 0) return VX_ERR_INVALID_ARG;
   dim3 block(256), grid(ceil_div(num_nodes, 8), ceil_div(N, 32 * EPL));
-  vx_tile_rows_kernel<T><<<grid, block, 0, stream>>>(blk_offsets, packed, hind, num_nodes, N, B, C, epi);
+  if (!vec_access_ok(N, EPL, B, C))
+    vx_spmm_tile_rows_kernel<T, ScalarAccess<T>><<<dim3(grid.x, ceil_div(N, 32)), block, 0, stream>>>(
+        blk_offsets, packed, hind, num_nodes, N, B, C, epi);
+  else
+    vx_spmm_tile_rows_kernel<T><<<grid, block, 0, stream>>>(blk_offsets, packed, hind, num_nodes, N, B, C, epi);
   VX_LAUNCH_CHECK();
   return VX_OK;
 }

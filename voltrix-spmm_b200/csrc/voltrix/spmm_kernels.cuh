@@ -39,6 +39,8 @@ struct SpmmPlan {
                                          // differs for a row shard of A, whose columns span the full matrix
   void *split_ws = nullptr;              // model 3: bf16 [input_rows][2 * embedding_dim] workspace
   Epilogue epilogue;                     // optional fused row scale / bias / ReLU (default: none)
+  int32_t *ticket = nullptr;             // 4 bytes the tensor-core kernel claims its work units from (atomic ticket; one
+                                         // per stream in flight); null = static striding over the work list
 };
 
 template <typename T> struct TcSupported { static constexpr bool value = false; };
@@ -60,7 +62,7 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
         if (plan.num_fixups > 0 && plan.scratch == nullptr) return VX_ERR_INVALID_ARG;
         rc = launch_spmm_tc<T, STAGES, NPW>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
                                        hspa_packed, hind, num_nodes, b_rows, embedding_dim, input,
-                                       output, plan.scratch, stream, plan.epilogue);
+                                       output, plan.scratch, stream, plan.epilogue, plan.ticket);
         if (rc != VX_OK) return rc;
         if (plan.num_sparse_rows > 0) {
           if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows) return VX_ERR_INVALID_ARG;
@@ -69,7 +71,7 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
         }
       } else {
         rc = launch_spmm_tc<T, STAGES, NPW>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind, num_nodes, b_rows,
-                                       embedding_dim, input, output, nullptr, stream, plan.epilogue);
+                                       embedding_dim, input, output, nullptr, stream, plan.epilogue, plan.ticket);
       }
       return rc;
     } else {
@@ -94,7 +96,7 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
         rc = launch_spmm_tc<__nv_bfloat16, STAGES, NPW, 2>(plan.items, plan.num_items, plan.fixups, plan.num_fixups,
                                                            blks_offsets, hspa_packed, hind, num_nodes, b_rows,
                                                            embedding_dim, terms, output, plan.scratch, stream,
-                                                           plan.epilogue);
+                                                           plan.epilogue, plan.ticket);
         if (rc != VX_OK) return rc;
         if (plan.num_sparse_rows > 0) {   // sparse windows: exact fp32 rows from the original operand
           if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows) return VX_ERR_INVALID_ARG;
@@ -104,7 +106,7 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
       } else {
         rc = launch_spmm_tc<__nv_bfloat16, STAGES, NPW, 2>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind,
                                                            num_nodes, b_rows, embedding_dim, terms, output, nullptr,
-                                                           stream, plan.epilogue);
+                                                           stream, plan.epilogue, plan.ticket);
       }
       return rc;
     } else {

@@ -25,11 +25,12 @@
 //     producers never wait on a global load;
 //   * full/empty mbarriers per stage (tcgen05.commit frees a stage when the MMAs that read it retire),
 //     full/empty per metadata chunk, full/empty per TMEM accumulator;
-//   * persistent CTAs stride over the LPT-sorted work list (schedule.cuh), every role derives the same
-//     item sequence independently, so no intra-CTA work broadcast is needed;
+//   * persistent CTAs claim units (feature tile, item) from the LPT-sorted work list (schedule.cuh) with an atomic
+//     ticket, feature-tile-major; the loader lane is the CTA's scheduler and publishes each unit to the other
+//     roles through a small shared-memory ring (static striding when the caller passes no ticket counter);
 //   * TERMS = 2 (fp32 input as two bf16 terms) doubles the gathered tile and the MMAs of a K-step, same accumulator;
 //   * the optional Epilogue (row scale / bias / ReLU) is applied to whole-window items here and to K-split windows in
-//     vx_fixup_kernel.
+//     vx_spmm_fixup_kernel.
 // What paces it (measured, profiles/r1c_bottleneck_isolation.md): a 128x16x16 MMA costs ~68 clk back to back, TMA writes 32
 // and the tensor core reads 36 shared-memory wavefronts per K-step, and the L2 slices deliver the gather at 86 % of their
 // peak at best -- three floors of 61-68 clk per K-step; the kernel runs at ~79.
@@ -88,6 +89,8 @@ struct TcGeom {
   static constexpr int kMmaWarp = kEpilogueWarp0 + 4, kLoaderWarp = kEpilogueWarp0 + 5;
   static constexpr int kThreads = (kEpilogueWarp0 + 6) * 32;
   static constexpr uint32_t kTmemCols = 32;             // two 16-column accumulators
+  static constexpr int kUnitSlots = 4;                  // work-unit ring (loader -> every other role), 32 B per slot
+  static constexpr int kUnitConsumers = NPW + 5;        // producer warps + MMA warp + 4 epilogue warps
 };
 
 // KSTEPS = K-steps in flight (the autotuned "stages" knob): ring depth = KSTEPS / NPW stages.
@@ -96,7 +99,8 @@ constexpr size_t tc_smem_bytes() {
   using G = TcGeom<NPW, TERMS>;
   constexpr int S = KSTEPS / G::kKsPerStage;
   return size_t(S) * (G::kStageB + G::kStageA) + size_t(G::kMetaSlots) * (G::kMetaH + G::kMetaP) +
-         (2 * S + 2 * G::kMetaSlots + 4) * 8 + 16 + 128 /*nibble table*/ + 1024 /*align slack*/;
+         (2 * S + 2 * G::kMetaSlots + 4 + 2 * G::kUnitSlots) * 8 + 16 + 128 /*nibble table*/ + G::kUnitSlots * 32 +
+         1024 /*align slack*/;
 }
 
 template <typename T, int KSTEPS, int NPW, int TERMS = 1>
@@ -104,28 +108,32 @@ __global__ void __launch_bounds__(TcGeom<NPW, TERMS>::kThreads, 1)
 vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__restrict__ items, int32_t num_items,
                   int32_t n_feat_tiles, const int32_t *__restrict__ blk_offsets, const uint4 *__restrict__ packed,
                   const int4 *__restrict__ hind4, int32_t num_nodes, int32_t N, float *__restrict__ C,
-                  float *__restrict__ scratch, int32_t term_stride, Epilogue epi) {
+                  float *__restrict__ scratch, int32_t term_stride, Epilogue epi, int32_t *__restrict__ ticket) {
   using G = TcGeom<NPW, TERMS>;
   static_assert(NPW % G::kKsPerStage == 0, "producer warps must form whole groups");
   static_assert(KSTEPS % G::kKsPerStage == 0 && KSTEPS / G::kKsPerStage > G::kGroups,
                 "the ring must hold more stages than there are producer groups");
   constexpr uint32_t S = KSTEPS / G::kKsPerStage;
   constexpr uint32_t MR = G::kMetaSlots;
+  constexpr uint32_t UR = G::kUnitSlots;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sB = sbase;                               // [S][4 K-steps][4096]  1024-aligned atoms
   const uint32_t sA = sB + S * G::kStageB;                 // [S][4 K-steps][512]
   const uint32_t sMetaH = sA + S * G::kStageA;             // [MR][64 blocks][8 int32]
   const uint32_t sMetaP = sMetaH + MR * G::kMetaH;         // [MR][64 blocks][4 uint32]
-  const uint32_t sBar = sMetaP + MR * G::kMetaP;           // full[S] empty[S] mfull[MR] mempty[MR] tfull[2] tempty[2]
-  const uint32_t sTmem = sBar + (2 * S + 2 * MR + 4) * 8;
+  const uint32_t sBar = sMetaP + MR * G::kMetaP;           // full[S] empty[S] mfull[MR] mempty[MR] tfull[2] tempty[2] ufull[UR] uempty[UR]
+  const uint32_t sTmem = sBar + (2 * S + 2 * MR + 4 + 2 * UR) * 8;
   const uint32_t sLut = sTmem + 16;                        // [16] nibble -> four 16-bit {0, 1.0} values (8 B each)
+  const uint32_t sUnit = sLut + 128;                       // [UR] {WorkItem, feature-tile base, valid}
   auto full_bar = [&](uint32_t s) { return sBar + s * 8; };
   auto empty_bar = [&](uint32_t s) { return sBar + (S + s) * 8; };
   auto mfull_bar = [&](uint32_t m) { return sBar + (2 * S + m) * 8; };
   auto mempty_bar = [&](uint32_t m) { return sBar + (2 * S + MR + m) * 8; };
   auto tfull_bar = [&](uint32_t a) { return sBar + (2 * S + 2 * MR + a) * 8; };
   auto tempty_bar = [&](uint32_t a) { return sBar + (2 * S + 2 * MR + 2 + a) * 8; };
+  auto ufull_bar = [&](uint32_t q) { return sBar + (2 * S + 2 * MR + 4 + q) * 8; };
+  auto uempty_bar = [&](uint32_t q) { return sBar + (2 * S + 2 * MR + 4 + UR + q) * 8; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t total_units = num_items * n_feat_tiles;
@@ -138,6 +146,18 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
     it.blk_count = blk_offsets[i + 1] - it.blk_begin;
     it.slot = -1;
     return it;
+  };
+  // Every role but the loader learns its next unit from the unit ring (whole warp; lane 0 frees the slot).
+  auto next_unit = [&](uint32_t &uc, WorkItem &it, int32_t &c_base) -> bool {
+    const uint32_t q = uc % UR;
+    ptx::mbar_wait(ufull_bar(q), (uc / UR) & 1u);
+    const int4 a = ptx::lds128(sUnit + q * 32), b = ptx::lds128(sUnit + q * 32 + 16);
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(uempty_bar(q));
+    ++uc;
+    it.window = a.x; it.blk_begin = a.y; it.blk_count = a.z; it.slot = a.w;
+    c_base = b.x;
+    return b.y != 0;
   };
 
   if (warp == G::kMmaWarp) {
@@ -153,6 +173,10 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
       for (uint32_t a = 0; a < 2; ++a) {
         ptx::mbar_init(tfull_bar(a), 1);               // tcgen05.commit after the item's last MMA
         ptx::mbar_init(tempty_bar(a), 4);              // one arrive per epilogue warp
+      }
+      for (uint32_t q = 0; q < UR; ++q) {
+        ptx::mbar_init(ufull_bar(q), 1);               // loader publishes a unit
+        ptx::mbar_init(uempty_bar(q), G::kUnitConsumers);   // every consumer warp has read it
       }
       ptx::fence_mbar_init();
     }
@@ -175,12 +199,33 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
 
   if (warp == G::kLoaderWarp) {
-    // ------------------------------------------------------------------ metadata loader (one lane)
+    // ------------------------------------------------------------------ scheduler + metadata loader (one lane)
+    // Units are (feature tile, item) pairs, feature-tile-major: all items of one 128-feature column slice of B before
+    // the next slice, so that only one slice has to stay L2-resident at a time.  Within a slice the items come in LPT
+    // order.  With a ticket counter every CTA claims its next unit with one atomicAdd (claimed one unit ahead, so the
+    // round trip to L2 hides behind the current unit's metadata stream); without one, CTAs stride over the list.
     if (ptx::elect_one()) {
       const uint64_t pol = ptx::policy_evict_first();   // hind / bitmaps are streamed once: do not displace B in L2
-      uint32_t gc = 0;
-      for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const WorkItem it = load_item(u / n_feat_tiles);
+      uint32_t gc = 0, uc = 0;
+      int32_t u = blockIdx.x;
+      int32_t ahead = ticket != nullptr ? int32_t(gridDim.x) + atomicAdd(ticket, 1) : u + int32_t(gridDim.x);
+      for (;;) {
+        const uint32_t q = uc % UR;
+        ptx::mbar_wait(uempty_bar(q), ((uc / UR) & 1u) ^ 1u);
+        const bool valid = u < total_units;
+        WorkItem it;
+        it.window = 0; it.blk_begin = 0; it.blk_count = 0; it.slot = -1;
+        int32_t c_base = 0;
+        if (valid) {
+          const int32_t tile = u / num_items;
+          it = load_item(u - tile * num_items);
+          c_base = tile * G::kFeatTile;
+        }
+        ptx::sts128(sUnit + q * 32, uint32_t(it.window), uint32_t(it.blk_begin), uint32_t(it.blk_count), uint32_t(it.slot));
+        ptx::sts128(sUnit + q * 32 + 16, uint32_t(c_base), valid ? 1u : 0u, 0u, 0u);
+        ptx::mbar_arrive(ufull_bar(q));   // release: the two stores above are visible to whoever sees the phase flip
+        ++uc;
+        if (!valid) break;
         for (int32_t b0 = 0; b0 < it.blk_count; b0 += G::kChunkBlks, ++gc) {
           const uint32_t m = gc % MR;
           const uint32_t nb = uint32_t(min(G::kChunkBlks, it.blk_count - b0));
@@ -189,6 +234,8 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
           ptx::bulk_g2s_hint(sMetaH + m * G::kMetaH, hind4 + int64_t(it.blk_begin + b0) * 2, nb * 32u, mfull_bar(m), pol);
           ptx::bulk_g2s_hint(sMetaP + m * G::kMetaP, packed + int64_t(it.blk_begin + b0), nb * 16u, mfull_bar(m), pol);
         }
+        u = ahead;
+        ahead = ticket != nullptr ? int32_t(gridDim.x) + atomicAdd(ticket, 1) : u + int32_t(gridDim.x);
       }
     }
   } else if (warp < NPW) {
@@ -201,11 +248,24 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
     const int grp = warp / G::kKsPerStage;  // stages st with st % kGroups == grp are this warp's
     const uint32_t a_off = uint32_t(kw) * G::kKsA + (n >> 3) * 256 + kc * 128 + (n & 7) * 16;
     const uint32_t p_off = uint32_t(2 * kw + kc) * 16 + uint32_t(n >> 3) * 4, shift = uint32_t(n & 7) << 2;
-    uint32_t s = 0, par = 0, m = 0, mpar = 0;
+    uint32_t s = 0, par = 0, m = 0, mpar = 0, uc = 0;
     int32_t turn = 0;                       // global stage counter mod kGroups
-    for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const WorkItem it = load_item(u / n_feat_tiles);
-      const int32_t c_base = (u % n_feat_tiles) * G::kFeatTile;
+#ifdef VX_TC_HUB_POPC
+    // L2-policy probe (R-MAT ids: a column's expected degree falls with the number of set bits of its id): gathers whose
+    // four rows are all "hub" rows are tagged evict_last, the rest evict_first.
+    const uint64_t pol_hot = ptx::policy_evict_last(), pol_cold = ptx::policy_evict_first();
+#endif
+    auto g4 = [&](uint32_t d, uint32_t bar, int32_t c, const int4 &r) {
+#ifdef VX_TC_HUB_POPC
+      const bool hot = max(max(__popc(r.x), __popc(r.y)), max(__popc(r.z), __popc(r.w))) <= VX_TC_HUB_POPC;
+      ptx::tma_gather4_hint(d, &tmap, bar, c, r.x, r.y, r.z, r.w, hot ? pol_hot : pol_cold);
+#else
+      ptx::tma_gather4(d, &tmap, bar, c, r.x, r.y, r.z, r.w);
+#endif
+    };
+    WorkItem it;
+    int32_t c_base;
+    while (next_unit(uc, it, c_base)) {
       const int32_t c1 = c_base + G::kAtomCols;
       const bool two_halves = c1 < N;
       const int32_t nks = (it.blk_count + 1) >> 1;
@@ -254,14 +314,14 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
               for (int t = 0; t < TERMS; ++t) {   // term t: columns shifted by t * term_stride, tile t of the K-step
                 const uint32_t d = dst + t * G::kTermB;
                 const int32_t ca = c_base + t * term_stride, cb = c1 + t * term_stride;
-                ptx::tma_gather4(d, &tmap, bar, ca, r0.x, r0.y, r0.z, r0.w);
-                ptx::tma_gather4(d + 1024, &tmap, bar, cb, r0.x, r0.y, r0.z, r0.w);
-                ptx::tma_gather4(d + 512, &tmap, bar, ca, r1.x, r1.y, r1.z, r1.w);
-                ptx::tma_gather4(d + 1536, &tmap, bar, cb, r1.x, r1.y, r1.z, r1.w);
-                ptx::tma_gather4(d + 2048, &tmap, bar, ca, r2.x, r2.y, r2.z, r2.w);
-                ptx::tma_gather4(d + 3072, &tmap, bar, cb, r2.x, r2.y, r2.z, r2.w);
-                ptx::tma_gather4(d + 2560, &tmap, bar, ca, r3.x, r3.y, r3.z, r3.w);
-                ptx::tma_gather4(d + 3584, &tmap, bar, cb, r3.x, r3.y, r3.z, r3.w);
+                g4(d, bar, ca, r0);
+                g4(d + 1024, bar, cb, r0);
+                g4(d + 512, bar, ca, r1);
+                g4(d + 1536, bar, cb, r1);
+                g4(d + 2048, bar, ca, r2);
+                g4(d + 3072, bar, cb, r2);
+                g4(d + 2560, bar, ca, r3);
+                g4(d + 3584, bar, cb, r3);
               }
             } else {
               const int4 r0 = ptx::lds128(ha), r1 = ptx::lds128(ha + 16);
@@ -272,15 +332,15 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
               for (int t = 0; t < TERMS; ++t) {
                 const uint32_t d = dst + t * G::kTermB;
                 const int32_t ca = c_base + t * term_stride, cb = c1 + t * term_stride;
-                ptx::tma_gather4(d, &tmap, bar, ca, r0.x, r0.y, r0.z, r0.w);
-                ptx::tma_gather4(d + 512, &tmap, bar, ca, r1.x, r1.y, r1.z, r1.w);
-                ptx::tma_gather4(d + 2048, &tmap, bar, ca, r2.x, r2.y, r2.z, r2.w);
-                ptx::tma_gather4(d + 2560, &tmap, bar, ca, r3.x, r3.y, r3.z, r3.w);
+                g4(d, bar, ca, r0);
+                g4(d + 512, bar, ca, r1);
+                g4(d + 2048, bar, ca, r2);
+                g4(d + 2560, bar, ca, r3);
                 if (two_halves) {
-                  ptx::tma_gather4(d + 1024, &tmap, bar, cb, r0.x, r0.y, r0.z, r0.w);
-                  ptx::tma_gather4(d + 1536, &tmap, bar, cb, r1.x, r1.y, r1.z, r1.w);
-                  ptx::tma_gather4(d + 3072, &tmap, bar, cb, r2.x, r2.y, r2.z, r2.w);
-                  ptx::tma_gather4(d + 3584, &tmap, bar, cb, r3.x, r3.y, r3.z, r3.w);
+                  g4(d + 1024, bar, cb, r0);
+                  g4(d + 1536, bar, cb, r1);
+                  g4(d + 3072, bar, cb, r2);
+                  g4(d + 3584, bar, cb, r3);
                 }
               }
             }
@@ -302,9 +362,10 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
   } else if (warp == G::kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = ptx::make_idesc(TcFmt<T>::kFmt, /*A MN-major*/ true, /*B K-major*/ false, 128, 16);
-    uint32_t s = 0, par = 0, unit = 0;
-    for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const WorkItem it = load_item(u / n_feat_tiles);
+    uint32_t s = 0, par = 0, unit = 0, uc = 0;
+    WorkItem it;
+    int32_t c_base;
+    while (next_unit(uc, it, c_base)) {
       const int32_t nks = (it.blk_count + 1) >> 1;
       if (nks == 0) continue;
       const int32_t nst = (nks + G::kKsPerStage - 1) / G::kKsPerStage;
@@ -354,10 +415,11 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
   } else if (warp >= G::kEpilogueWarp0 && warp < G::kEpilogueWarp0 + 4) {
     // ------------------------------------------------------------------ epilogue: TMEM -> C
     const int ew = warp - G::kEpilogueWarp0;   // == warp % 4: the TMEM lane quarter this warp may read
-    uint32_t unit = 0;
-    for (int32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const WorkItem it = load_item(u / n_feat_tiles);
-      const int32_t f = (u % n_feat_tiles) * G::kFeatTile + ew * 32 + lane;
+    uint32_t unit = 0, uc = 0;
+    WorkItem it;
+    int32_t c_base;
+    while (next_unit(uc, it, c_base)) {
+      const int32_t f = c_base + ew * 32 + lane;
       uint32_t v[16];
       if (it.blk_count > 0) {
         const uint32_t acc = unit & 1u;
@@ -402,7 +464,7 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
 }
 
 // Sums the partial tiles of K-split windows in slot order (fixed order => deterministic).
-__global__ void vx_fixup_kernel(const FixupItem *__restrict__ fixups, int32_t num_fixups,
+__global__ void vx_spmm_fixup_kernel(const FixupItem *__restrict__ fixups, int32_t num_fixups,
                                 const float *__restrict__ scratch, int32_t num_nodes, int32_t N,
                                 float *__restrict__ C, Epilogue epi) {
   const int32_t i = blockIdx.x;
@@ -475,7 +537,7 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
                           const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind,
                           int32_t num_nodes, int64_t b_rows,
                           int32_t N, const T *B, float *C, float *scratch, cudaStream_t stream,
-                          const Epilogue &epi = Epilogue()) {
+                          const Epilogue &epi = Epilogue(), int32_t *ticket = nullptr) {
   if (num_items <= 0) return VX_OK;
   if (N % 8 != 0 || (reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(hind) & 15) ||
       (reinterpret_cast<uintptr_t>(hspa_packed) & 15))
@@ -493,19 +555,23 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
   const int32_t n_feat_tiles = ceil_div(N, G::kFeatTile);
   const int64_t total_units = int64_t(num_items) * n_feat_tiles;
   const int grid = int(total_units < device_sm_count() ? total_units : device_sm_count());
+  // `ticket` (4 bytes of device memory owned by the caller, one per stream in flight): dynamic unit claiming.
+  // Zeroed here, on the stream, so a launch never depends on how the previous one ended; nullptr = static striding.
+  if (ticket != nullptr) VX_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int32_t), stream));
   kern<<<grid, G::kThreads, smem, stream>>>(tmap, items, num_items, n_feat_tiles, blk_offsets,
                                                  reinterpret_cast<const uint4 *>(hspa_packed),
-                                                 reinterpret_cast<const int4 *>(hind), num_nodes, N, C, scratch, N, epi);
+                                                 reinterpret_cast<const int4 *>(hind), num_nodes, N, C, scratch, N, epi,
+                                                 ticket);
   VX_LAUNCH_CHECK();
   if (num_fixups > 0) {
-    vx_fixup_kernel<<<num_fixups, 256, 0, stream>>>(fixups, num_fixups, scratch, num_nodes, N, C, epi);
+    vx_spmm_fixup_kernel<<<num_fixups, 256, 0, stream>>>(fixups, num_fixups, scratch, num_nodes, N, C, epi);
     VX_LAUNCH_CHECK();
   }
   return VX_OK;
 }
 
 // fp32 -> [hi | lo] bf16 terms: out[r, c] = bf16(x), out[r, N + c] = bf16(x - hi).  One thread per 4 values.
-__global__ void vx_split_bf16x2_kernel(const float4 *__restrict__ in, __nv_bfloat16 *__restrict__ out, int64_t rows,
+__global__ void vx_spmm_split_bf16x2_kernel(const float4 *__restrict__ in, __nv_bfloat16 *__restrict__ out, int64_t rows,
                                        int32_t N) {
   const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;   // quad index
   const int32_t qpr = N >> 2;
@@ -518,7 +584,9 @@ __global__ void vx_split_bf16x2_kernel(const float4 *__restrict__ in, __nv_bfloa
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     hi[i] = __float2bfloat16_rn(x[i]);
-    lo[i] = __float2bfloat16_rn(x[i] - __bfloat162float(hi[i]));
+    // Inf, or a finite value that rounds to bf16 Inf: the high term alone carries it (x - hi would be Inf - Inf = NaN)
+    const float h = __bfloat162float(hi[i]);
+    lo[i] = __float2bfloat16_rn(isfinite(h) ? x[i] - h : 0.f);
   }
   __nv_bfloat16 *o = out + r * (2 * int64_t(N)) + c;
   *reinterpret_cast<uint2 *>(o) = *reinterpret_cast<const uint2 *>(hi);
@@ -530,7 +598,7 @@ inline int launch_split_bf16x2(const float *in, __nv_bfloat16 *out, int64_t rows
     return VX_ERR_UNSUPPORTED;
   const int64_t quads = rows * (N >> 2);
   if (quads <= 0) return VX_OK;
-  vx_split_bf16x2_kernel<<<unsigned((quads + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4 *>(in), out,
+  vx_spmm_split_bf16x2_kernel<<<unsigned((quads + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4 *>(in), out,
                                                                             rows, N);
   VX_LAUNCH_CHECK();
   return VX_OK;

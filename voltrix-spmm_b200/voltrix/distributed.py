@@ -75,6 +75,37 @@ def shard_csr(indptr: torch.Tensor, indices: torch.Tensor, r0: int, r1: int) -> 
     return (indptr[r0:r1 + 1] - lo).to(torch.int32).contiguous(), indices[lo:hi].contiguous()
 
 
+def operand_slices(rows: int, world: int) -> Tuple[int, List[Tuple[int, int]]]:
+    """Equal row slices of the dense operand for the per-step exchange: ``chunk = ceil(rows / world)`` rows per rank (what
+    an all-gather needs), the last ranks' slices clipped to ``rows`` (possibly empty).  Returns ``(chunk, [(lo, hi)])``."""
+    chunk = (rows + world - 1) // world
+    return chunk, [(min(r * chunk, rows), min((r + 1) * chunk, rows)) for r in range(world)]
+
+
+def upload_slice_and_all_gather(buf: torch.Tensor, feat_host: torch.Tensor, rank: int, world: int, group=None) -> torch.Tensor:
+    """The per-step exchange of a host-resident dense operand (north_star: "B is broadcast over NVLink with NCCL"):
+    every rank copies only ITS 1/world row slice of ``feat_host`` (pinned host memory on a GPU box) into ``buf`` and the
+    ranks all-gather the slices in place, so each step moves the operand ONCE over the host links (1/world per GPU) and
+    the rest over NVLink.  ``buf``: ``[chunk * world, N]`` on the compute device; returns ``buf[:rows]``.  Runs on the
+    current stream (the NCCL work is ordered after the copy and before whatever the caller enqueues next)."""
+    rows = feat_host.shape[0]
+    chunk, slices = operand_slices(rows, world)
+    assert buf.shape[0] == chunk * world and buf.shape[1:] == feat_host.shape[1:]
+    lo, hi = slices[rank]
+    if hi > lo:
+        buf[lo:hi].copy_(feat_host[lo:hi], non_blocking=True)
+    if world > 1:
+        mine = buf[rank * chunk:(rank + 1) * chunk]
+        if buf.is_cuda:
+            dist.all_gather_into_tensor(buf, mine, group=group)      # in place: `mine` is buf's own slot of this rank
+        else:
+            parts = [torch.empty_like(mine) for _ in range(world)]   # gloo (CPU tests): no in-place flat gather
+            dist.all_gather(parts, mine.clone(), group=group)
+            for r, part in enumerate(parts):
+                buf[r * chunk:(r + 1) * chunk].copy_(part)
+    return buf[:rows]
+
+
 class ShardedSpMM:
     """Per-rank state of a row-sharded SpMM.
 
@@ -83,9 +114,13 @@ class ShardedSpMM:
     stand-ins to exercise the partitioning / collective logic under gloo.
     """
 
-    def __init__(self, indptr: torch.Tensor, indices: torch.Tensor, num_nodes: int,
+    def __init__(self, indptr: Optional[torch.Tensor], indices: Optional[torch.Tensor], num_nodes: int,
                  weights: Optional[torch.Tensor] = None, group=None,
-                 local_preprocess: Optional[Callable] = None, local_spmm: Optional[Callable] = None):
+                 local_preprocess: Optional[Callable] = None, local_spmm: Optional[Callable] = None,
+                 local_csr: Optional[Callable] = None):
+        """Either the whole CSR matrix (``indptr``, ``indices``; every rank holds it and cuts out its shard), or -- for
+        graphs no single rank should materialise -- per-row ``weights`` for the partition plus ``local_csr(r0, r1) ->
+        (indptr, indices)``, which builds just this rank's rows (column ids global)."""
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -98,7 +133,11 @@ class ShardedSpMM:
         self.ranges = partition_rows(weights, self.world)
         self.r0, self.r1 = self.ranges[self.rank]
         self.local_rows = self.r1 - self.r0
-        lp, li = shard_csr(indptr, indices, self.r0, self.r1)
+        if local_csr is not None:
+            lp, li = local_csr(self.r0, self.r1)
+            assert lp.numel() == self.local_rows + 1
+        else:
+            lp, li = shard_csr(indptr, indices, self.r0, self.r1)
         self.local_nnz = int(li.numel())
         if local_preprocess is None:
             from .spmm import csr_preprocess
@@ -122,18 +161,39 @@ class ShardedSpMM:
             return torch.empty((0, feat.shape[1]), dtype=torch.float32, device=feat.device)
         return self._spmm(self.state, feat)
 
-    def all_gather(self, c_local: torch.Tensor) -> torch.Tensor:
-        """Optional: full C on every rank.  Shards are padded to the largest row count."""
+    def all_gather(self, c_local: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Optional: full C ``[num_nodes, N]`` on every rank.  Every rank sends exactly its own rows (grouped
+        point-to-point sends inside one NCCL group call -- no padding to the largest shard and no concatenation pass);
+        ``out`` lets the caller reuse the result buffer across steps."""
         if self.world == 1:
             return c_local
         n = c_local.shape[1]
-        max_rows = max(b - a for a, b in self.ranges)
-        padded = torch.zeros((max_rows, n), dtype=c_local.dtype, device=c_local.device)
-        padded[: c_local.shape[0]] = c_local
-        out = torch.empty((self.world, max_rows, n), dtype=c_local.dtype, device=c_local.device)
-        dist.all_gather_into_tensor(out.view(-1, n), padded, group=self.group) if c_local.is_cuda else \
-            dist.all_gather(list(out.unbind(0)), padded, group=self.group)
-        return torch.cat([out[k, : b - a] for k, (a, b) in enumerate(self.ranges)], 0)
+        if out is None:
+            out = torch.empty((self.num_nodes, n), dtype=c_local.dtype, device=c_local.device)
+        parts = [out[a:b] for a, b in self.ranges]
+        peer = (lambda k: dist.get_global_rank(self.group, k)) if self.group is not None else (lambda k: k)
+        if c_local.is_cuda:
+            # uneven all-gather: NCCL runs the world x world sends / receives as one fused group
+            ops = []
+            for k in range(self.world):
+                if k == self.rank:
+                    continue
+                if self.local_rows > 0:
+                    ops.append(dist.P2POp(dist.isend, c_local, peer(k), self.group))
+                if parts[k].shape[0] > 0:
+                    ops.append(dist.P2POp(dist.irecv, parts[k], peer(k), self.group))
+            parts[self.rank].copy_(c_local)
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+        else:
+            for k in range(self.world):   # gloo (CPU tests): one broadcast per shard
+                if parts[k].shape[0] == 0:
+                    continue
+                if k == self.rank:
+                    parts[k].copy_(c_local)
+                dist.broadcast(parts[k], src=peer(k), group=self.group)
+        return out
 
     def imbalance(self, weights: Sequence[float]) -> float:
         """max / mean of per-rank weights (1.0 = perfect)."""

@@ -36,6 +36,7 @@ plan.split_ws = split_ws;
 plan.epilogue.row_scale = row_scale;
 plan.epilogue.bias = bias;
 plan.epilogue.relu = relu;
+plan.ticket = ticket;
 __return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}, {npw}>(
     blk_offsets, hspa_packed, hind,
     num_nodes, num_edges, embedding_dim, input, output, {model}, plan, stream);
@@ -76,26 +77,55 @@ def arg_defs_for(dtype):
         ("row_scale", torch.float32),
         ("bias", torch.float32),
         ("relu", int),
+        ("ticket", torch.int32),
         ("stream", torch.cuda.Stream),
     )
 
 
-def _split_workspace(owner, rows: int, embedding_dim: int, device) -> torch.Tensor:
-    """bf16 [rows, 2 * embedding_dim] buffer for the fp32 tensor-core path (model 3), cached on the plan (or on
-    ``hspa_packed`` when the caller came with a bare reference triple)."""
-    cache = getattr(owner, "_vx_split_ws", None)
+def _owner_cache(owner, attr: str) -> dict:
+    cache = getattr(owner, attr, None)
     if cache is None:
         cache = {}
         try:
-            owner._vx_split_ws = cache
+            setattr(owner, attr, cache)
         except AttributeError:
             pass
-    key = (rows, embedding_dim, str(device))
+    return cache
+
+
+def _split_workspace(owner, rows: int, embedding_dim: int, device, stream_id: int) -> torch.Tensor:
+    """bf16 [rows, 2 * embedding_dim] buffer for the fp32 tensor-core path (model 3), cached on the plan (or on
+    ``hspa_packed`` when the caller came with a bare reference triple), one per CUDA stream: two SpMMs on the same
+    matrix from different streams must not share it."""
+    cache = _owner_cache(owner, "_vx_split_ws")
+    key = (rows, embedding_dim, str(device), stream_id)
     buf = cache.get(key)
     if buf is None:
         buf = torch.empty((rows, 2 * embedding_dim), dtype=torch.bfloat16, device=device)
         cache[key] = buf
     return buf
+
+
+def _ticket(owner, device, stream_id: int) -> torch.Tensor:
+    """The 4-byte work-claim counter of the tensor-core kernel (zeroed by every launch, on its stream), one per
+    (matrix, stream)."""
+    cache = _owner_cache(owner, "_vx_ticket")
+    key = (str(device), stream_id)
+    buf = cache.get(key)
+    if buf is None:
+        buf = torch.zeros(4, dtype=torch.int32, device=device)
+        cache[key] = buf
+    return buf
+
+
+def fp32_space():
+    """Autotune space for fp32 input.  Model 3 (two bf16 terms on the tensor cores, ~16 mantissa bits) is left out when
+    ``VOLTRIX_FP32_EXACT=1``: then only the exact-fp32 CUDA-core models compete and fp32 results do not depend on which
+    candidate happened to be fastest on this machine."""
+    import os
+    if os.environ.get("VOLTRIX_FP32_EXACT", "0") == "1":
+        return tuple(c for c in SPACE_FP32 if c["model"] != 3)
+    return SPACE_FP32
 
 
 def feature_hash(feature: torch.Tensor) -> str:
@@ -147,15 +177,20 @@ def spmm_kernel(
 
     if plan is None:
         plan = getattr(hspa_packed, "_vx_plan", None)
-    p = plan.launch_args(embedding_dim) if plan is not None else (None, 0, None, 0, None, None, None, None, 0)
+    stream = current_stream()
+    sid = int(stream.cuda_stream)
+    p = plan.launch_args(embedding_dim, sid) if plan is not None else (None, 0, None, 0, None, None, None, None, 0)
     if model is not None:   # explicit variant (tests, benchmarks): a space of one, no timing runs
         stages = int(stages or (24 if int(model) == 3 else 32))
         npw = int(npw or {8: 4, 16: 4, 36: 12, 42: 14, 40: 24}.get(stages, 8))
         space = ({"model": int(model), "stages": stages, "npw": npw},)
         keys = {"ctype": _CTYPE[input.dtype], "fixed": f"{model}/{stages}/{npw}"}
     else:
-        space = SPACE_FP32 if input.dtype == torch.float32 else SPACE_HALF
-        keys = {"ctype": _CTYPE[input.dtype], "feature_hash": feature_hash(hspa_packed), "N": embedding_dim}
+        space = fp32_space() if input.dtype == torch.float32 else SPACE_HALF
+        # the key also says what the plan can do: a winner found with the CSR arrays (model 1) or a work list must not
+        # be replayed on a matrix that came without them under the same user-chosen hash_tag
+        caps = ("p" if plan is not None else "-") + ("c" if plan is not None and plan.csr_indptr is not None else "-")
+        keys = {"ctype": _CTYPE[input.dtype], "feature_hash": feature_hash(hspa_packed), "N": embedding_dim, "plan": caps}
 
     # fp32 on the tensor cores (model 3) needs a bf16 [rows, 2N] workspace: hand it over while that model is still a
     # candidate for this key, drop it once the tuner has settled on a CUDA-core model
@@ -165,9 +200,10 @@ def spmm_kernel(
     split_ws = None
     if input.dtype == torch.float32 and embedding_dim % 8 == 0 and any(c["model"] == 3 for c in space) and \
             (winner is None or winner.get("model") == 3):
-        split_ws = _split_workspace(ws_owner, int(input.shape[0]), embedding_dim, input.device)
+        split_ws = _split_workspace(ws_owner, int(input.shape[0]), embedding_dim, input.device, sid)
+    ticket = _ticket(ws_owner, input.device, sid)
     args = (blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, input, output, *p,
-            int(input.shape[0]), split_ws, row_scale, bias, int(bool(relu)), current_stream())
+            int(input.shape[0]), split_ws, row_scale, bias, int(bool(relu)), ticket, stream)
 
     runtime = jit_tuner.compile_and_tune(
         name="spmm_kernel",

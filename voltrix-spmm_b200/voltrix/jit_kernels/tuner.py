@@ -123,7 +123,9 @@ class JITTuner:
             for code, tuned_keys in cands:
                 if tuned_keys == want:
                     runtime, _, err = _build_one(name, arg_defs, code, tuned_keys)
-                    if runtime is not None:
+                    # the persisted winner gets the same validity run a fresh candidate gets: if it cannot run these
+                    # arguments (a matrix without the CSR arrays under a shared hash_tag, ...) fall through and re-tune
+                    if runtime is not None and runtime(*args) == 0:
                         self.tuned[signature] = runtime
                         self.tuned_keys[signature] = tuned_keys
                         return runtime

@@ -70,19 +70,21 @@ class SpmmPlan:
     def signature(self) -> str:
         return f"M{self.num_nodes}_E{self.num_edges}_B{self.total_blocks}_I{self.num_items}_S{self.num_sparse_rows}"
 
-    def scratch(self, embedding_dim: int) -> Optional[torch.Tensor]:
+    def scratch(self, embedding_dim: int, stream_id: int = 0) -> Optional[torch.Tensor]:
+        """Partial-tile buffer of the K-split windows, one per (N, CUDA stream): launches on different streams may be in
+        flight together and must not share partial tiles (the reference's spmm is stream-safe)."""
         if self.num_slots == 0:
             return None
-        buf = self._scratch.get(embedding_dim)
+        buf = self._scratch.get((embedding_dim, stream_id))
         if buf is None:
             buf = torch.empty(self.num_slots * BLK_H * embedding_dim, dtype=torch.float32, device=self.items.device)
-            self._scratch[embedding_dim] = buf
+            self._scratch[(embedding_dim, stream_id)] = buf
         return buf
 
-    def launch_args(self, embedding_dim: int):
+    def launch_args(self, embedding_dim: int, stream_id: int = 0):
         """The plan part of the spmm ``launch`` argument list (see jit_kernels/spmm.py::arg_defs_for)."""
         return (self.items, self.num_items, self.fixups if self.num_fixups else None, self.num_fixups,
-                self.scratch(embedding_dim), self.csr_indptr, self.csr_indices,
+                self.scratch(embedding_dim, stream_id), self.csr_indptr, self.csr_indices,
                 self.sparse_rows if self.num_sparse_rows else None, self.num_sparse_rows)
 
 
@@ -109,7 +111,19 @@ def csr_preprocess(
 
     num_edges = indices.numel()
     num_row_windows = math.ceil(num_nodes / BLK_H)
-    num_cols = int(num_cols) if num_cols is not None else num_nodes
+    # The sort key packs [window | column | row-in-window] with just enough column bits for ``num_cols``: an id outside
+    # [0, num_cols) would spill into the window field and send the scatter kernel out of bounds.  The reference's
+    # std::map compaction takes any non-negative id (a rectangular A through the 3-argument signature), so the column
+    # range is measured here (one reduction; the host sync below exists anyway) rather than assumed.
+    if num_edges > 0:
+        lo, hi = (int(v) for v in torch.aminmax(indices))
+        if lo < 0:
+            raise ValueError(f"csr_preprocess: negative column index {lo}")
+        if num_cols is not None and hi >= int(num_cols):
+            raise ValueError(f"csr_preprocess: column index {hi} out of range for num_cols={int(num_cols)}")
+    else:
+        hi = -1
+    num_cols = int(num_cols) if num_cols is not None else max(num_nodes, hi + 1)
 
     # phase 1: (window, column) sort, distinct-column ranks, TC blocks per window
     workspace = alloc_workspace(preprocess_workspace_bytes(num_edges, num_nodes), dev)
@@ -249,12 +263,13 @@ class HostStreamedSpMM:
     """
 
     def __init__(self, blk_offsets, hspa_packed, hind, num_nodes: int, num_edges: int, num_feats: int,
-                 dtype=torch.float16, input_rows: Optional[int] = None, depth: int = 2, shard_upload: bool = False,
-                 group=None):
-        """``shard_upload`` (multi-GPU, one process per GPU, torch.distributed initialised): every rank uploads only its
-        1/world slice of the dense operand and the ranks all-gather it over NVLink (NCCL) instead of each pulling the whole
-        operand through the host's PCIe.  EXPERIMENTAL: written at the end of round 1 without GPU time left to run it;
-        off by default."""
+                 dtype=torch.float16, input_rows: Optional[int] = None, depth: int = 2,
+                 shard_upload: Optional[bool] = None, group=None):
+        """``shard_upload`` (multi-GPU, one process per GPU): every rank uploads only its 1/world row slice of the dense
+        operand and the ranks all-gather the slices over NVLink (NCCL) on the copy-in stream, instead of each rank pulling
+        the whole operand through the host links (``voltrix.distributed.upload_slice_and_all_gather``).  Default (None):
+        on whenever torch.distributed is initialised with more than one rank.  Every rank must then ``submit`` the same
+        number of steps (the all-gather is a collective)."""
         require_cuda()
         dev = hspa_packed.device
         self.state = (blk_offsets, hspa_packed, hind)
@@ -262,9 +277,9 @@ class HostStreamedSpMM:
         rows = input_rows if input_rows is not None else num_nodes
         self.rows = rows
         self.group, self.world, self.rank = group, 1, 0
-        if shard_upload:
+        if shard_upload is None or shard_upload:
             import torch.distributed as dist
-            if dist.is_initialized() and dist.get_world_size(group) > 1:
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
                 self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.chunk = (rows + self.world - 1) // self.world          # all-gather needs equal slices: pad the last one
         self.feat_dev = [torch.empty(self.chunk * self.world, num_feats, dtype=dtype, device=dev) for _ in range(depth)]
@@ -291,12 +306,8 @@ class HostStreamedSpMM:
             if self.world == 1:
                 self.feat_dev[b].copy_(feat_host, non_blocking=True)
             else:
-                import torch.distributed as dist
-                lo, hi = self.rank * self.chunk, min((self.rank + 1) * self.chunk, self.rows)
-                if hi > lo:
-                    self.feat_dev[b][lo:hi].copy_(feat_host[lo:hi], non_blocking=True)
-                mine = self.feat_dev[b][self.rank * self.chunk: (self.rank + 1) * self.chunk]
-                dist.all_gather_into_tensor(self.feat_dev[b], mine, group=self.group)   # in place, on s_in
+                from ..distributed import upload_slice_and_all_gather
+                upload_slice_and_all_gather(self.feat_dev[b], feat_host, self.rank, self.world, self.group)
             self.ev_in[b].record(self.s_in)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(self.ev_in[b])
