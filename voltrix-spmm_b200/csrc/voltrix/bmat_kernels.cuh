@@ -378,6 +378,64 @@ inline int hmat_packed_swizzle_cuda(int32_t num_row_windows, const int32_t *Poin
   return VX_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Value tiles (no reference counterpart: the reference's format is binary, bmat_kernels.cuh:100-103).
+// For a CSR matrix WITH values the tensor-core kernel reads, per TC block, a 16 x 8 tile of 16-bit values laid out
+// as the shared-memory image of its A^T operand chunk: element (row r, column slot c) at (r >> 3) * 64 + (r & 7) * 8 + c
+// (in elements; 128 elements = 256 bytes per block).  One thread per stored entry, in CSR order: the entry's slot is
+// found by binary search for its column among the window's compacted columns in `hind` (sorted ascending; the zero
+// padding after the last real column of a window's last block compares as +infinity).  A (row, col) pair stored twice
+// would need an atomic add on a 16-bit value: the caller passes coalesced input (csr_preprocess counts duplicates).
+// ------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T vx_from_float(float v);
+template <> __device__ __forceinline__ __half vx_from_float<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 vx_from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void vx_value_tiles_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                      const float *__restrict__ values, int32_t num_nodes, int64_t nnz,
+                                      const int32_t *__restrict__ pointer1, const int32_t *__restrict__ hind,
+                                      T *__restrict__ tiles, int32_t *__restrict__ not_found) {
+  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  const int32_t row = vx_row_of_edge(indptr, num_nodes, e);
+  const int32_t w = row >> 4, col = __ldg(indices + e);
+  const int64_t b0 = pointer1[w];
+  const int32_t slots = (pointer1[w + 1] - int32_t(b0)) * BLK_W;
+  const int32_t *u = hind + b0 * BLK_W;
+  int32_t lo = 0, hi = slots;      // first slot whose column is >= col
+  while (lo < hi) {
+    const int32_t mid = lo + ((hi - lo) >> 1);
+    const int32_t v = __ldg(u + mid);
+    const bool less = (mid > 0 && v == 0) ? false : (uint32_t(v) < uint32_t(col));   // padding zeros sort last
+    if (less) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= slots || u[lo] != col) {   // the triple does not belong to this CSR matrix
+    atomicAdd(not_found, 1);
+    return;
+  }
+  const int64_t b = b0 + (lo >> 3);
+  const int32_t r = row & 15, c = lo & 7;
+  tiles[b * (BLK_H * BLK_W) + (r >> 3) * 64 + (r & 7) * 8 + c] = vx_from_float<T>(__ldg(values + e));
+}
+
+// tiles: T [total_blocks * 128], zeroed here; not_found (device int32, zeroed here) counts entries whose column is not in
+// the tile format (a mismatched triple) -- the caller checks it.
+template <typename T>
+inline int value_tiles(const int32_t *indptr, const int32_t *indices, const float *values, int32_t num_nodes,
+                       int64_t nnz, const int32_t *pointer1, const int32_t *hind, int64_t total_blocks, T *tiles,
+                       int32_t *not_found, cudaStream_t stream) {
+  if (num_nodes < 0 || nnz < 0 || total_blocks < 0 || not_found == nullptr) return VX_ERR_INVALID_ARG;
+  VX_CUDA_TRY(cudaMemsetAsync(not_found, 0, sizeof(int32_t), stream));
+  if (total_blocks > 0) VX_CUDA_TRY(cudaMemsetAsync(tiles, 0, size_t(total_blocks) * BLK_H * BLK_W * sizeof(T), stream));
+  if (nnz > 0) {
+    vx_value_tiles_kernel<T><<<grid_for(nnz, 256), 256, 0, stream>>>(indptr, indices, values, num_nodes, nnz, pointer1,
+                                                                     hind, tiles, not_found);
+    VX_LAUNCH_CHECK();
+  }
+  return VX_OK;
+}
+
 }  // namespace voltrix
 
 #endif  // VOLTRIX_B200_BMAT_KERNELS_CUH_

@@ -325,37 +325,38 @@ inline int launch_csr_rows(const int32_t *indptr, const int32_t *indices, const 
   return VX_OK;
 }
 
-// General CSR SpMM with fp32 values (duplicated (row, col) entries add up, as in any CSR product).
+// General CSR SpMM with fp32 values (duplicated (row, col) entries add up, as in any CSR product).  `row_list` (optional):
+// compute only those rows (the sparse windows of a weighted tensor-core SpMM); num_edges < 0 = mean degree unknown.
 template <typename T>
 inline int launch_csr_rows_weighted(const int32_t *indptr, const int32_t *indices, const float *vals, int32_t num_rows,
                                     int64_t num_edges, int32_t N, const T *B, float *C, cudaStream_t stream,
-                                    const Epilogue &epi = Epilogue()) {
+                                    const Epilogue &epi = Epilogue(), const int32_t *row_list = nullptr) {
   constexpr int EPL = Vec16<T>::N;
   if (num_rows <= 0) return VX_OK;
   if (vals == nullptr || N <= 0) return VX_ERR_INVALID_ARG;
   if (!vec_access_ok(N, EPL, B, C)) {
     vx_spmm_csr_rows_kernel<T, 32, true, ScalarAccess<T>><<<dim3(ceil_div(num_rows, 8), ceil_div(N, 32)), dim3(256), 0, stream>>>(
-        indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+        indptr, indices, row_list, num_rows, N, B, C, epi, vals);
     VX_LAUNCH_CHECK();
     return VX_OK;
   }
   const int lanes_needed = N / EPL;
   const int lanes = lanes_needed <= 4 ? 4 : lanes_needed <= 8 ? 8 : lanes_needed <= 16 ? 16 : 32;
-  const float mean_degree = float(num_edges) / float(num_rows);
+  const float mean_degree = num_edges >= 0 ? float(num_edges) / float(num_rows) : 1e30f;
   dim3 block(256);
   if (lanes < 32 && mean_degree < 4.f * float(32 / lanes)) {
     dim3 g(unsigned(ceil_div<int64_t>(int64_t(num_rows) * lanes, 256)), ceil_div(N, lanes * EPL));
-    if (lanes == 4)      vx_spmm_csr_subwarp_rows_kernel<T, 4, true><<<g, block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
-    else if (lanes == 8) vx_spmm_csr_subwarp_rows_kernel<T, 8, true><<<g, block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
-    else                 vx_spmm_csr_subwarp_rows_kernel<T, 16, true><<<g, block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+    if (lanes == 4)      vx_spmm_csr_subwarp_rows_kernel<T, 4, true><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi, vals);
+    else if (lanes == 8) vx_spmm_csr_subwarp_rows_kernel<T, 8, true><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi, vals);
+    else                 vx_spmm_csr_subwarp_rows_kernel<T, 16, true><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi, vals);
     VX_LAUNCH_CHECK();
     return VX_OK;
   }
   auto grid = [&](int l) { return dim3(ceil_div(num_rows, 8), ceil_div(N, l * EPL)); };
-  if (lanes == 4)       vx_spmm_csr_rows_kernel<T, 4, true><<<grid(4), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
-  else if (lanes == 8)  vx_spmm_csr_rows_kernel<T, 8, true><<<grid(8), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
-  else if (lanes == 16) vx_spmm_csr_rows_kernel<T, 16, true><<<grid(16), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
-  else                  vx_spmm_csr_rows_kernel<T, 32, true><<<grid(32), block, 0, stream>>>(indptr, indices, nullptr, num_rows, N, B, C, epi, vals);
+  if (lanes == 4)       vx_spmm_csr_rows_kernel<T, 4, true><<<grid(4), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi, vals);
+  else if (lanes == 8)  vx_spmm_csr_rows_kernel<T, 8, true><<<grid(8), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi, vals);
+  else if (lanes == 16) vx_spmm_csr_rows_kernel<T, 16, true><<<grid(16), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi, vals);
+  else                  vx_spmm_csr_rows_kernel<T, 32, true><<<grid(32), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi, vals);
   VX_LAUNCH_CHECK();
   return VX_OK;
 }

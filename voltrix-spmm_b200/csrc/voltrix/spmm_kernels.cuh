@@ -39,6 +39,8 @@ struct SpmmPlan {
                                          // differs for a row shard of A, whose columns span the full matrix
   void *split_ws = nullptr;              // model 3: bf16 [input_rows][2 * embedding_dim] workspace
   Epilogue epilogue;                     // optional fused row scale / bias / ReLU (default: none)
+  const void *value_tiles = nullptr;     // WEIGHTED: 16-bit value tiles, 256 B per TC block (bmat_kernels.cuh::value_tiles)
+  const float *csr_values = nullptr;     // WEIGHTED: fp32 values in CSR order (CUDA-core rows: sparse windows, model 1)
   int32_t *ticket = nullptr;             // 4 bytes the tensor-core kernel claims its work units from (atomic ticket; one
                                          // per stream in flight); null = static striding over the work list
 };
@@ -47,12 +49,49 @@ template <typename T> struct TcSupported { static constexpr bool value = false; 
 template <> struct TcSupported<__half> { static constexpr bool value = true; };
 template <> struct TcSupported<__nv_bfloat16> { static constexpr bool value = true; };
 
-template <typename T, int STAGES = 32, int NPW = 8>
+// A with per-edge values (no reference counterpart): model 0 runs the WEIGHTED instantiation of
+// the tensor-core kernel on plan.value_tiles (+ weighted CUDA-core rows for the sparse windows), model 1 the weighted
+// CUDA-core rows on plan.csr_values.  16-bit dense operands ride the tensor cores; fp32 operands use model 1.
+template <typename T, int STAGES, int NPW>
+inline int voltrix_spmm_weighted_forward_cuda(const int32_t *blks_offsets, const int32_t *hind, int num_nodes,
+                                              int num_edges, int embedding_dim, const T *input, float *output, int model,
+                                              const SpmmPlan &plan, cudaStream_t stream) {
+  const int64_t b_rows = plan.input_rows > 0 ? plan.input_rows : num_nodes;
+  if (model == 0) {
+    if constexpr (TcSupported<T>::value) {
+      if (plan.items == nullptr || plan.value_tiles == nullptr) return VX_ERR_INVALID_ARG;
+      if (plan.num_fixups > 0 && plan.scratch == nullptr) return VX_ERR_INVALID_ARG;
+      int rc = launch_spmm_tc<T, STAGES, NPW, 1, true>(plan.items, plan.num_items, plan.fixups, plan.num_fixups,
+                                                       blks_offsets, static_cast<const uint32_t *>(plan.value_tiles), hind,
+                                                       num_nodes, b_rows, embedding_dim, input, output, plan.scratch,
+                                                       stream, plan.epilogue, plan.ticket);
+      if (rc != VX_OK) return rc;
+      if (plan.num_sparse_rows > 0) {
+        if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows || !plan.csr_values) return VX_ERR_INVALID_ARG;
+        rc = launch_csr_rows_weighted<T>(plan.csr_indptr, plan.csr_indices, plan.csr_values, plan.num_sparse_rows, -1,
+                                         embedding_dim, input, output, stream, plan.epilogue, plan.sparse_rows);
+      }
+      return rc;
+    } else {
+      return VX_ERR_UNSUPPORTED;
+    }
+  } else if (model == 1) {
+    if (!plan.csr_indptr || !plan.csr_indices || !plan.csr_values) return VX_ERR_INVALID_ARG;
+    return launch_csr_rows_weighted<T>(plan.csr_indptr, plan.csr_indices, plan.csr_values, num_nodes, num_edges,
+                                       embedding_dim, input, output, stream, plan.epilogue);
+  }
+  return VX_ERR_UNSUPPORTED;
+}
+
+template <typename T, int STAGES = 32, int NPW = 8, bool WEIGHTED = false>
 inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t *hspa_packed, const int32_t *hind,
                                      int num_nodes, int num_edges, int embedding_dim, const T *input, float *output,
                                      int model, const SpmmPlan &plan, cudaStream_t stream) {
   if (num_nodes < 0 || embedding_dim <= 0) return VX_ERR_INVALID_ARG;
   if (num_nodes == 0) return VX_OK;
+  if constexpr (WEIGHTED)
+    return voltrix_spmm_weighted_forward_cuda<T, STAGES, NPW>(blks_offsets, hind, num_nodes, num_edges, embedding_dim,
+                                                              input, output, model, plan, stream);
   const int32_t W = ceil_div<int32_t>(num_nodes, BLK_H);
   const int64_t b_rows = plan.input_rows > 0 ? plan.input_rows : num_nodes;
   if (model == 0) {

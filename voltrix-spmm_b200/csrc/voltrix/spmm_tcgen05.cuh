@@ -103,7 +103,11 @@ constexpr size_t tc_smem_bytes() {
          1024 /*align slack*/;
 }
 
-template <typename T, int KSTEPS, int NPW, int TERMS = 1>
+// WEIGHTED: A carries per-edge values.  `packed` then points at VALUE TILES instead of bitmaps: 256 B per TC block,
+// element (row r, column slot c) of type T at (r >> 3) * 128 + (r & 7) * 16 + c * 2 -- exactly the K-major shared-memory image
+// of one 8-column chunk of the A^T operand (core matrices 128 B apart along the window rows, 256 B apart along K), so a
+// K-step's A^T tile is ONE 512-byte bulk copy from global memory into the stage and the producers expand nothing.
+template <typename T, int KSTEPS, int NPW, int TERMS = 1, bool WEIGHTED = false>
 __global__ void __launch_bounds__(TcGeom<NPW, TERMS>::kThreads, 1)
 vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__restrict__ items, int32_t num_items,
                   int32_t n_feat_tiles, const int32_t *__restrict__ blk_offsets, const uint4 *__restrict__ packed,
@@ -113,6 +117,7 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
   static_assert(NPW % G::kKsPerStage == 0, "producer warps must form whole groups");
   static_assert(KSTEPS % G::kKsPerStage == 0 && KSTEPS / G::kKsPerStage > G::kGroups,
                 "the ring must hold more stages than there are producer groups");
+  static_assert(!WEIGHTED || TERMS == 1, "per-edge values ride on the 16-bit path only");
   constexpr uint32_t S = KSTEPS / G::kKsPerStage;
   constexpr uint32_t MR = G::kMetaSlots;
   constexpr uint32_t UR = G::kUnitSlots;
@@ -230,9 +235,10 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
           const uint32_t m = gc % MR;
           const uint32_t nb = uint32_t(min(G::kChunkBlks, it.blk_count - b0));
           ptx::mbar_wait(mempty_bar(m), ((gc / MR) & 1u) ^ 1u);
-          ptx::mbar_arrive_expect_tx(mfull_bar(m), nb * 48u);
+          ptx::mbar_arrive_expect_tx(mfull_bar(m), WEIGHTED ? nb * 32u : nb * 48u);
           ptx::bulk_g2s_hint(sMetaH + m * G::kMetaH, hind4 + int64_t(it.blk_begin + b0) * 2, nb * 32u, mfull_bar(m), pol);
-          ptx::bulk_g2s_hint(sMetaP + m * G::kMetaP, packed + int64_t(it.blk_begin + b0), nb * 16u, mfull_bar(m), pol);
+          if (!WEIGHTED)   // value tiles do not go through the metadata ring: they land in the stage itself
+            ptx::bulk_g2s_hint(sMetaP + m * G::kMetaP, packed + int64_t(it.blk_begin + b0), nb * 16u, mfull_bar(m), pol);
         }
         u = ahead;
         ahead = ticket != nullptr ? int32_t(gridDim.x) + atomicAdd(ticket, 1) : u + int32_t(gridDim.x);
@@ -288,15 +294,23 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
           const bool has_b1 = ks < full_ks;                 // odd block count: the item's last K-step is half empty
           // A^T fragment of this lane: 8 K values (one TC block's 8 columns) of window row n, via the nibble table
 #if VX_TC_EXP != 5
-          uint32_t lo = 0, hi = 0;
-          if (has_b1 || kc == 0) {
-            lo = (ptx::lds32(pa) >> shift) & 0xfu;          // columns 0..3 of row n
-            hi = (ptx::lds32(pa + 8) >> shift) & 0xfu;      // columns 4..7
+          if constexpr (!WEIGHTED) {
+            uint32_t lo = 0, hi = 0;
+            if (has_b1 || kc == 0) {
+              lo = (ptx::lds32(pa) >> shift) & 0xfu;          // columns 0..3 of row n
+              hi = (ptx::lds32(pa + 8) >> shift) & 0xfu;      // columns 4..7
+            }
+            const uint2 e0 = ptx::lds64(sLut + lo * 8), e1 = ptx::lds64(sLut + hi * 8);
+            ptx::sts128(sA + s * G::kStageA + a_off, e0.x, e0.y, e1.x, e1.y);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+          } else if (!has_b1) {
+            // odd block count: the K-step's second 8-column chunk does not exist -- zero its 256 bytes (the gathered
+            // padding rows must meet zeros), the first chunk arrives by bulk copy below
+            if (lane < 16) ptx::sts128(sA + s * G::kStageA + uint32_t(kw) * G::kKsA + 256 + lane * 16, 0u, 0u, 0u, 0u);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
           }
-          const uint2 e0 = ptx::lds64(sLut + lo * 8), e1 = ptx::lds64(sLut + hi * 8);
-          ptx::sts128(sA + s * G::kStageA + a_off, e0.x, e0.y, e1.x, e1.y);
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
 #endif
 #if VX_TC_DBG == 2
           if (lane == 0) ptx::mbar_arrive(bar);
@@ -309,7 +323,10 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
             if (has_b1 && two_halves) {
               const int4 r0 = ptx::lds128(ha), r1 = ptx::lds128(ha + 16), r2 = ptx::lds128(ha + 32),
                          r3 = ptx::lds128(ha + 48);
-              ptx::mbar_arrive_expect_tx(bar, uint32_t(G::kKsB));
+              ptx::mbar_arrive_expect_tx(bar, uint32_t(G::kKsB) + (WEIGHTED ? 512u : 0u));
+              if constexpr (WEIGHTED)
+                ptx::bulk_g2s(sA + s * G::kStageA + uint32_t(kw) * G::kKsA, packed + (int64_t(it.blk_begin) + 2 * ks) * 16,
+                              512u, bar);
 #pragma unroll
               for (int t = 0; t < TERMS; ++t) {   // term t: columns shifted by t * term_stride, tile t of the K-step
                 const uint32_t d = dst + t * G::kTermB;
@@ -327,7 +344,11 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
               const int4 r0 = ptx::lds128(ha), r1 = ptx::lds128(ha + 16);
               int4 r2 = make_int4(0, 0, 0, 0), r3 = make_int4(0, 0, 0, 0);   // tail: row 0, bitmap bits are 0
               if (has_b1) { r2 = ptx::lds128(ha + 32); r3 = ptx::lds128(ha + 48); }
-              ptx::mbar_arrive_expect_tx(bar, uint32_t(two_halves ? G::kKsB : G::kKsB / 2));
+              const uint32_t vbytes = WEIGHTED ? (has_b1 ? 512u : 256u) : 0u;
+              ptx::mbar_arrive_expect_tx(bar, uint32_t(two_halves ? G::kKsB : G::kKsB / 2) + vbytes);
+              if constexpr (WEIGHTED)
+                ptx::bulk_g2s(sA + s * G::kStageA + uint32_t(kw) * G::kKsA, packed + (int64_t(it.blk_begin) + 2 * ks) * 16,
+                              vbytes, bar);
 #pragma unroll
               for (int t = 0; t < TERMS; ++t) {
                 const uint32_t d = dst + t * G::kTermB;
@@ -383,7 +404,9 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
           // Only the 14-bit start-address field changes from K-step to K-step (+4096 B / +512 B, no carry out of
           // the field: shared memory is < 256 KB), so the low words are advanced by constants.
           const uint64_t a_desc = ptx::smem_desc(sB + s * G::kStageB, 1024, 2048, ptx::kLayoutSw128);
-          const uint64_t b_desc = ptx::smem_desc(sA + s * G::kStageA, 128, 256, ptx::kLayoutNone);
+          // (value tiles: one TC block = 256 contiguous bytes, so k-chunk stride 256 and 8-row group stride 128)
+          const uint64_t b_desc = WEIGHTED ? ptx::smem_desc(sA + s * G::kStageA, 256, 128, ptx::kLayoutNone)
+                                           : ptx::smem_desc(sA + s * G::kStageA, 128, 256, ptx::kLayoutNone);
           const uint32_t a_lo = uint32_t(a_desc), a_hi = uint32_t(a_desc >> 32);
           const uint32_t b_lo = uint32_t(b_desc), b_hi = uint32_t(b_desc >> 32);
 #if VX_TC_DBG == 1
@@ -532,7 +555,7 @@ inline int device_sm_count() {
 // Launch the tensor-core kernel over a prepared work list.  B must be 16-byte aligned with N % 8 == 0
 // (TMA global-stride rule); hind / hspa_packed must be 16-byte aligned.
 // `B` holds TERMS column blocks of N elements per row (row stride TERMS * N): plain fp16 / bf16 input has TERMS = 1.
-template <typename T, int STAGES, int NPW, int TERMS = 1>
+template <typename T, int STAGES, int NPW, int TERMS = 1, bool WEIGHTED = false>
 inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupItem *fixups, int32_t num_fixups,
                           const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind,
                           int32_t num_nodes, int64_t b_rows,
@@ -546,7 +569,7 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
   int rc = make_gather_tensor_map(&tmap, B, TcFmt<T>::kTmapType, 2, b_rows, int64_t(N) * TERMS);
   if (rc != VX_OK) return rc;
   using G = TcGeom<NPW, TERMS>;
-  auto kern = vx_spmm_tc_kernel<T, STAGES, NPW, TERMS>;
+  auto kern = vx_spmm_tc_kernel<T, STAGES, NPW, TERMS, WEIGHTED>;
   constexpr size_t smem = tc_smem_bytes<STAGES, NPW, TERMS>();
   static_assert(smem <= 227 * 1024, "stage ring does not fit in shared memory");
   // Set on every launch (~1 us): a function-local `static bool` would be a GNU_UNIQUE symbol shared by every
