@@ -114,6 +114,11 @@ typedef struct {
    * take the next unit of the LPT list when they finish one).  One per stream that may have a launch in flight; zeroed by
    * vx_spmm on `stream`.  NULL = static striding over the list. */
   int32_t *ticket;
+  /* ABI v5: A with a value per stored entry (NULL / NULL = the reference's binary A).  value_tiles: what vx_value_tiles
+   * wrote, in `input`'s 16-bit dtype; read by model 0 in place of hspa_packed.  csr_values: fp32 [nnz] in the order of
+   * csr_indices; read by model 1 and by model 0's CUDA-core rows for sparse windows. */
+  const void *value_tiles;
+  const float *csr_values;
 } vx_plan_t;
 
 /* `stages` (models 0 and 3) = K-steps of 16 gathered rows kept in flight; it selects a compiled variant, each with its
@@ -122,6 +127,16 @@ typedef struct {
 int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind, int32_t num_nodes,
             int32_t num_edges, int32_t embedding_dim, const void *input, int32_t input_dtype, float *output,
             int32_t model, int32_t stages, const vx_plan_t *plan, void *stream);
+
+/* ---- per-edge values for the tensor-core path (no reference counterpart: the reference's tiles are binary,
+ * bmat_kernels.cuh:100-103) ----
+ * tiles: `tile_dtype` (VX_DTYPE_F16 / VX_DTYPE_BF16) [total_blocks * 128]: per TC block a 16 x 8 tile, element (row r,
+ * column slot c) at (r / 8) * 64 + (r % 8) * 8 + c.  Zeroed, then every stored entry of the coalesced CSR matrix is
+ * rounded into its slot (the slot is found by binary search in the window's hind list).  not_found (device int32[1]):
+ * number of stored entries without a slot -- non-zero means the triple does not belong to this matrix. */
+int vx_value_tiles(const int32_t *indptr, const int32_t *indices, const float *values, int32_t num_nodes,
+                   int64_t num_edges, const int32_t *blk_offsets, const int32_t *hind, int64_t total_blocks,
+                   void *tiles, int32_t tile_dtype, int32_t *not_found, void *stream);
 
 /* ---- general CSR x dense with fp32 values (no reference counterpart: its format is binary, bmat_kernels.cuh:102) ----
  * output[r, :] = act(row_scale[r] * sum_e values[e] * input[indices[e], :] + bias), CUDA-core rows, fp32 accumulate.

@@ -40,7 +40,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_host_only_queries(lib):
     lib.vx_abi_version.restype = ctypes.c_int
-    assert lib.vx_abi_version() == 5   # 5: vx_plan_t.ticket (dynamic unit claiming); 4: vx_spmm_csr_weighted; 2: vx_plan_t gained split_ws (fp32 tensor-core path); 3: fused epilogue fields
+    assert lib.vx_abi_version() == 5   # 5: vx_plan_t.ticket (dynamic unit claiming), value_tiles / csr_values + vx_value_tiles; 4: vx_spmm_csr_weighted; 2: vx_plan_t gained split_ws (fp32 tensor-core path); 3: fused epilogue fields
     lib.vx_preprocess_workspace_bytes.restype = ctypes.c_size_t
     lib.vx_preprocess_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int32]
     small = lib.vx_preprocess_workspace_bytes(1000, 100)

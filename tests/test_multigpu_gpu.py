@@ -37,18 +37,24 @@ def _worker(rank, world, port, q):
         feats = [torch.randn(M, N, generator=g).half().pin_memory() for _ in range(4)]
         outs = [torch.empty(sh.local_rows, N).pin_memory() for _ in range(4)]
         pipe = voltrix.HostStreamedSpMM(*sh.state, sh.local_rows, sh.local_nnz, N, dtype=torch.float16, input_rows=M)
-        ok = pipe.world == world           # sharded upload is the default once torch.distributed has > 1 rank
+        flags = {"sharded_upload_is_default": pipe.world == world}   # once torch.distributed has > 1 rank
         for f, o in zip(feats, outs):
             pipe.submit(f, o)
         pipe.wait()
         full_state = voltrix.csr_preprocess(indptr, indices, M)          # the single-GPU computation, on every rank
-        for f, o in zip(feats, outs):
+        same_split = full_state[1]._vx_plan.cap == sh.state[1]._vx_plan.cap
+        for i, (f, o) in enumerate(zip(feats, outs)):
             fd = f.to(dev)
             want_local = sh.spmm(fd)                                       # resident operand, this rank's rows
-            ok = ok and torch.equal(o, want_local.cpu())
+            flags[f"e2e_equals_resident_{i}"] = torch.equal(o, want_local.cpu())
             want_full = voltrix.spmm(*full_state, M, E, fd)
-            ok = ok and torch.equal(sh.all_gather(want_local), want_full)  # uneven all-gather == 1-GPU result, bit for bit
-        q.put((rank, bool(ok), sh.ranges))
+            got_full = sh.all_gather(want_local)                           # uneven all-gather
+            # same windows, same per-window order: bit-identical to the 1-GPU result unless a hub window is K-split at a
+            # different chunk size (the cap follows the shard's block count), which only reorders an fp32 sum
+            flags[f"gathered_equals_single_gpu_{i}"] = (torch.equal(got_full, want_full) if same_split else
+                                                        bool(((got_full - want_full).abs().max() /
+                                                              want_full.abs().max()).item() < 1e-6))
+        q.put((rank, all(flags.values()), {k: v for k, v in flags.items() if not v} or str(sh.ranges)))
     finally:
         dist.destroy_process_group()
 
@@ -68,4 +74,4 @@ def test_sharded_upload_and_all_gather_match_single_gpu(world):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in results), results
-    assert len({str(r[2]) for r in results}) == 1
+    assert len({r[2] for r in results}) == 1, "every rank must compute the same partition"

@@ -199,3 +199,91 @@ def test_four_feature_tiles_with_k_split_and_sparse_rows(dtype):
                             stages=stages)
         assert torch.isfinite(o).all()
         assert _scaled_err(o.cpu().numpy(), want) <= (1e-4 if dtype == torch.float16 else 2e-5), (model, stages)
+
+
+def _weighted_case(dtype_exact=True, seed=5):
+    """The epilogue case (hub window -> K-split, ordinary windows, sparse windows -> CUDA-core rows, M % 16 != 0) with a value
+    per stored entry.  Values are multiples of 1/8 in [-4, 4]: exactly representable in fp16 AND bf16, so rounding them into
+    the 16-bit value tiles is lossless and the tensor-core result can be held to the same bar as the binary path."""
+    from test_spmm_gpu import _epilogue_case
+    indptr, indices, M = _epilogue_case()
+    rng = np.random.default_rng(seed)
+    vals = (rng.integers(-32, 33, size=indices.size) / 8.0).astype(np.float32)
+    vals[vals == 0] = 0.125
+    return indptr, indices, vals, M
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N", [64, 128, 256])
+def test_weighted_tensor_core_path_matches_scipy(dtype, N):
+    """A with per-edge values on the tcgen05 kernel (value tiles bulk-copied straight into the A^T operand stage) -- every
+    tensor-core variant, the weighted CUDA-core model and the autotuned entry point against scipy on the same operand;
+    with the fused epilogue; K-split windows and sparse windows included."""
+    import scipy.sparse as sp
+    import voltrix
+    indptr, indices, vals, M = _weighted_case()
+    E = indices.size
+    A = sp.csr_matrix((vals, indices, indptr), shape=(M, M))
+    feat = torch.from_numpy(np.random.default_rng(1).standard_normal((M, N)).astype(np.float32)).cuda().to(dtype)
+    want = A @ feat.float().cpu().numpy()
+    st = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
+    plan = st[1]._vx_plan
+    assert plan.num_fixups >= 1 and plan.num_sparse_rows > 0
+    w = voltrix.edge_weights(*st, torch.from_numpy(indptr), torch.from_numpy(indices), torch.from_numpy(vals))
+    got = voltrix.spmm(*st, M, E, feat, edge_weights=w)
+    assert torch.isfinite(got).all() and _scaled_err(got.cpu().numpy(), want) <= 1e-4
+    for model, stages, npw in [(0, 16, None), (0, 36, None), (0, 42, None), (0, 32, 16), (0, 40, None), (1, 32, None)]:
+        o = torch.full((M, N), float("nan"), device="cuda")
+        voltrix.spmm_kernel(*st, num_nodes=M, num_edges=E, embedding_dim=N, input=feat, output=o, model=model,
+                            stages=stages, npw=npw, edge_weights=w)
+        assert torch.isfinite(o).all(), (model, stages)
+        assert _scaled_err(o.cpu().numpy(), want) <= 1e-4, (model, stages, npw)
+    # fused epilogue on top of the weighted product
+    scale = torch.rand(M, device="cuda") + 0.5
+    bias = torch.randn(N, device="cuda")
+    o = voltrix.spmm(*st, M, E, feat, edge_weights=w, row_scale=scale, bias=bias, relu=True)
+    want2 = np.maximum(want * scale.cpu().numpy()[:, None] + bias.cpu().numpy()[None, :], 0.0)
+    assert _scaled_err(o.cpu().numpy(), want2) <= 1e-4
+    # the binary product of the same triple is untouched by the weights
+    plain = voltrix.spmm(*st, M, E, feat)
+    want_plain = sp.csr_matrix((np.ones(E, np.float32), indices, indptr), shape=(M, M)) @ feat.float().cpu().numpy()
+    assert _scaled_err(plain.cpu().numpy(), want_plain) <= 1e-4
+
+
+def test_weighted_fp32_operand_and_general_values():
+    """fp32 dense operand: the weighted product runs on the exact-fp32 CUDA-core rows.  General (not 16-bit representable)
+    values on the tensor cores are rounded to the operand's format: within fp16's 2^-11 of scipy."""
+    import scipy.sparse as sp
+    import voltrix
+    indptr, indices, _, M = _weighted_case()
+    E = indices.size
+    vals = np.random.default_rng(2).standard_normal(E).astype(np.float32)
+    A = sp.csr_matrix((vals, indices, indptr), shape=(M, M))
+    st = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
+    w = voltrix.edge_weights(*st, torch.from_numpy(indptr), torch.from_numpy(indices), torch.from_numpy(vals))
+    f32 = torch.from_numpy(np.random.default_rng(3).standard_normal((M, 128)).astype(np.float32)).cuda()
+    got = voltrix.spmm(*st, M, E, f32, edge_weights=w)
+    assert _scaled_err(got.cpu().numpy(), A @ f32.cpu().numpy()) <= 2e-5
+    f16 = f32.half()
+    o = torch.empty(M, 128, device="cuda")
+    voltrix.spmm_kernel(*st, num_nodes=M, num_edges=E, embedding_dim=128, input=f16, output=o, model=0, stages=42,
+                        edge_weights=w)
+    assert _scaled_err(o.cpu().numpy(), A @ f16.float().cpu().numpy()) <= 1e-3
+
+
+def test_edge_weights_refuses_foreign_triples_and_duplicates():
+    import voltrix
+    indptr, indices, vals, M = _weighted_case()
+    st = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
+    # a CSR matrix that is NOT the one the triple was built from: row 16 gets a column its window (rows 16..31) never had
+    window_cols = set(indices[indptr[16]:indptr[32]].tolist())
+    foreign = next(c for c in range(M) if c not in window_cols)
+    other = indices.copy()
+    row = other[indptr[16]:indptr[17]].copy(); row[0] = foreign; other[indptr[16]:indptr[17]] = np.sort(row)
+    w = voltrix.edge_weights(*st, torch.from_numpy(indptr), torch.from_numpy(other), torch.from_numpy(vals))
+    with pytest.raises(ValueError, match="no slot"):
+        w.tiles(torch.float16)
+    dup_ptr = np.array([0, 3], np.int32); dup_idx = np.array([1, 1, 2], np.int32)
+    st2 = voltrix.csr_preprocess(torch.from_numpy(dup_ptr), torch.from_numpy(dup_idx), 1, num_cols=4)
+    with pytest.raises(ValueError, match="more than once"):
+        voltrix.edge_weights(*st2, torch.from_numpy(dup_ptr), torch.from_numpy(dup_idx), torch.ones(3))

@@ -18,10 +18,13 @@ static int spmm_dispatch(const int32_t *blk_offsets, const uint32_t *hspa_packed
                          int32_t num_nodes, int32_t num_edges, int32_t embedding_dim, const void *input,
                          float *output, int32_t model, int32_t stages, const SpmmPlan &plan, cudaStream_t stream) {
   const T *in = static_cast<const T *>(input);
+  const bool weighted = plan.value_tiles != nullptr || plan.csr_values != nullptr;
   // `stages` = K-steps (16 gathered rows each) in flight; the number of producer warps follows from it
-#define VX_TC_VARIANT(KS, NPW)                                                                                   \
-  return voltrix_spmm_forward_cuda<T, KS, NPW>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, in, \
-                                               output, model, plan, stream)
+#define VX_TC_VARIANT(KS, NPW)                                                                                          \
+  return weighted ? voltrix_spmm_forward_cuda<T, KS, NPW, true>(blk_offsets, hspa_packed, hind, num_nodes, num_edges,   \
+                                                                embedding_dim, in, output, model, plan, stream)         \
+                  : voltrix_spmm_forward_cuda<T, KS, NPW>(blk_offsets, hspa_packed, hind, num_nodes, num_edges,         \
+                                                          embedding_dim, in, output, model, plan, stream)
   switch (stages) {
     case 8: VX_TC_VARIANT(8, 4);
     case 16: VX_TC_VARIANT(16, 4);
@@ -132,6 +135,8 @@ int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32
     p.epilogue.bias = plan->bias;
     p.epilogue.relu = plan->relu;
     p.ticket = plan->ticket;
+    p.value_tiles = plan->value_tiles;
+    p.csr_values = plan->csr_values;
   }
   cudaStream_t s = (cudaStream_t)stream;
   switch (input_dtype) {
@@ -145,6 +150,19 @@ int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32
       return spmm_dispatch<__nv_bfloat16>(blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, input,
                                           output, model, stages, p, s);
   }
+  return VX_ERR_INVALID_ARG;
+}
+
+int vx_value_tiles(const int32_t *indptr, const int32_t *indices, const float *values, int32_t num_nodes,
+                   int64_t num_edges, const int32_t *blk_offsets, const int32_t *hind, int64_t total_blocks, void *tiles,
+                   int32_t tile_dtype, int32_t *not_found, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (tile_dtype == VX_DTYPE_F16)
+    return value_tiles<__half>(indptr, indices, values, num_nodes, num_edges, blk_offsets, hind, total_blocks,
+                               static_cast<__half *>(tiles), not_found, s);
+  if (tile_dtype == VX_DTYPE_BF16)
+    return value_tiles<__nv_bfloat16>(indptr, indices, values, num_nodes, num_edges, blk_offsets, hind, total_blocks,
+                                      static_cast<__nv_bfloat16 *>(tiles), not_found, s);
   return VX_ERR_INVALID_ARG;
 }
 

@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 import torch
 
-from . import bmat_swizzle, hmat_gem, preprocess, spmm, spmm_csr, tiles
+from . import bmat_swizzle, hmat_gem, preprocess, spmm, spmm_csr, tiles, value_tiles
 from .tuner import jit_tuner
 
 
@@ -31,7 +31,14 @@ def all_variants():
     ]
     for dtype, ctype in spmm._CTYPE.items():
         space = spmm.SPACE_FP32 if dtype == torch.float32 else spmm.SPACE_HALF + spmm.EXTRA_HALF
-        out.append(("spmm_kernel", {"ctype": ctype}, space, spmm.includes, spmm.arg_defs_for(dtype), spmm.template))
+        out.append(("spmm_kernel", {"ctype": ctype, "weighted": "false"}, space, spmm.includes, spmm.arg_defs_for(dtype),
+                    spmm.template))
+        wspace = spmm.SPACE_FP32_WEIGHTED if dtype == torch.float32 else spmm.SPACE_HALF_WEIGHTED + ({"model": 0, "stages": 16, "npw": 4},)
+        out.append(("spmm_kernel", {"ctype": ctype, "weighted": "true"}, wspace, spmm.includes, spmm.arg_defs_for(dtype),
+                    spmm.template))
+        if dtype != torch.float32:
+            out.append(("value_tiles_kernel", {"ctype": ctype}, tuple(), value_tiles.includes, value_tiles.arg_defs_for(dtype),
+                        value_tiles.template))
         out.append(("spmm_csr_weighted_kernel", {"ctype": ctype}, tuple(), spmm_csr.includes, spmm_csr.arg_defs_for(dtype),
                     spmm_csr.template))
     return out

@@ -37,7 +37,9 @@ plan.epilogue.row_scale = row_scale;
 plan.epilogue.bias = bias;
 plan.epilogue.relu = relu;
 plan.ticket = ticket;
-__return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}, {npw}>(
+plan.value_tiles = value_tiles;
+plan.csr_values = csr_values;
+__return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}, {npw}, {weighted}>(
     blk_offsets, hspa_packed, hind,
     num_nodes, num_edges, embedding_dim, input, output, {model}, plan, stream);
 """
@@ -51,6 +53,11 @@ SPACE_HALF = ({"model": 0, "stages": 36, "npw": 12}, {"model": 0, "stages": 42, 
 EXTRA_HALF = ({"model": 0, "stages": 16, "npw": 4}, {"model": 0, "stages": 32, "npw": 8})
 # fp32: model 3 = tcgen05 on two bf16 terms (hi + lo); models 1 / 2 = exact-fp32 CUDA-core rows
 SPACE_FP32 = ({"model": 3, "stages": 24, "npw": 8}, {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
+
+
+# A with per-edge values: the WEIGHTED tensor-core instantiations and the weighted CUDA-core CSR rows
+SPACE_HALF_WEIGHTED = tuple(c for c in SPACE_HALF if c["model"] in (0, 1))
+SPACE_FP32_WEIGHTED = ({"model": 1, "stages": 32, "npw": 8},)
 
 
 def arg_defs_for(dtype):
@@ -78,6 +85,8 @@ def arg_defs_for(dtype):
         ("bias", torch.float32),
         ("relu", int),
         ("ticket", torch.int32),
+        ("value_tiles", dtype if dtype != torch.float32 else torch.float16),
+        ("csr_values", torch.float32),
         ("stream", torch.cuda.Stream),
     )
 
@@ -159,10 +168,12 @@ def spmm_kernel(
     row_scale=None,
     bias=None,
     relu=False,
+    edge_weights=None,
 ):
-    """Extensions beyond the reference's signature: ``plan`` / ``model`` / ``stages`` / ``npw`` (explicit variant), and the
+    """Extensions beyond the reference's signature: ``plan`` / ``model`` / ``stages`` / ``npw`` (explicit variant), the
     fused epilogue ``output = act(row_scale[:, None] * (A @ input) + bias[None, :])`` with fp32 ``row_scale [num_nodes]``,
-    fp32 ``bias [embedding_dim]`` and ``act`` = ReLU when ``relu`` (all optional, applied in the kernel that writes C)."""
+    fp32 ``bias [embedding_dim]`` and ``act`` = ReLU when ``relu`` (all optional, applied in the kernel that writes C), and
+    ``edge_weights`` (``voltrix.edge_weights(...)``): A carries a value per stored entry instead of 1."""
     assert blk_offsets.is_cuda and blk_offsets.dtype == torch.int32
     assert hspa_packed.is_cuda and hspa_packed.dtype == torch.uint32
     assert hind.is_cuda and hind.dtype == torch.int32
@@ -180,17 +191,31 @@ def spmm_kernel(
     stream = current_stream()
     sid = int(stream.cuda_stream)
     p = plan.launch_args(embedding_dim, sid) if plan is not None else (None, 0, None, 0, None, None, None, None, 0)
+    weighted = edge_weights is not None
+    value_tiles = csr_values = None
+    if weighted:
+        assert plan is not None and plan.items is not None, "edge_weights need the plan csr_preprocess attaches to hspa_packed"
+        csr_values = edge_weights.csr_values
+        assert csr_values.is_cuda and csr_values.dtype == torch.float32 and csr_values.numel() == num_edges
+        if input.dtype != torch.float32:   # the value tiles must be in the dense operand's 16-bit format
+            value_tiles = edge_weights.tiles(input.dtype)
+            assert value_tiles.numel() == plan.total_blocks * 128
     if model is not None:   # explicit variant (tests, benchmarks): a space of one, no timing runs
         stages = int(stages or (24 if int(model) == 3 else 32))
         npw = int(npw or {8: 4, 16: 4, 36: 12, 42: 14, 40: 24}.get(stages, 8))
         space = ({"model": int(model), "stages": stages, "npw": npw},)
         keys = {"ctype": _CTYPE[input.dtype], "fixed": f"{model}/{stages}/{npw}"}
+    elif weighted:
+        space = SPACE_FP32_WEIGHTED if input.dtype == torch.float32 else SPACE_HALF_WEIGHTED
+        keys = {"ctype": _CTYPE[input.dtype], "feature_hash": feature_hash(hspa_packed), "N": embedding_dim, "plan": "pcw"}
     else:
         space = fp32_space() if input.dtype == torch.float32 else SPACE_HALF
         # the key also says what the plan can do: a winner found with the CSR arrays (model 1) or a work list must not
         # be replayed on a matrix that came without them under the same user-chosen hash_tag
         caps = ("p" if plan is not None else "-") + ("c" if plan is not None and plan.csr_indptr is not None else "-")
         keys = {"ctype": _CTYPE[input.dtype], "feature_hash": feature_hash(hspa_packed), "N": embedding_dim, "plan": caps}
+
+    keys["weighted"] = "true" if weighted else "false"
 
     # fp32 on the tensor cores (model 3) needs a bf16 [rows, 2N] workspace: hand it over while that model is still a
     # candidate for this key, drop it once the tuner has settled on a CUDA-core model
@@ -203,7 +228,7 @@ def spmm_kernel(
         split_ws = _split_workspace(ws_owner, int(input.shape[0]), embedding_dim, input.device, sid)
     ticket = _ticket(ws_owner, input.device, sid)
     args = (blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, input, output, *p,
-            int(input.shape[0]), split_ws, row_scale, bias, int(bool(relu)), ticket, stream)
+            int(input.shape[0]), split_ws, row_scale, bias, int(bool(relu)), ticket, value_tiles, csr_values, stream)
 
     runtime = jit_tuner.compile_and_tune(
         name="spmm_kernel",

@@ -9,4 +9,6 @@ from .spmm import (
     save_preprocessed,
     load_preprocessed,
     spmm_gcn,
+    EdgeWeights,
+    edge_weights,
 )

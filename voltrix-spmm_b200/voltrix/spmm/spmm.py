@@ -22,6 +22,7 @@ from typing import Optional
 import torch
 
 from ..jit_kernels import (
+    value_tiles_kernel,
     csr_tiles_scatter_kernel,
     csr_window_sort_kernel,
     preprocess_workspace_bytes,
@@ -39,6 +40,8 @@ BLK_W = 8
 # A window goes to the CUDA-core row path when gathering its nnz rows one by one moves fewer than
 # SPARSE_RATIO x the rows the tensor-core path would gather for it (16 per K-step).
 DEFAULT_SPARSE_RATIO = 0.5
+# Longest run of TC blocks one work item accumulates in the tensor core before its partial tile is handed to the fix-up pass.
+MAX_CHAIN_BLOCKS = 2048
 
 
 class SpmmPlan:
@@ -155,9 +158,12 @@ def csr_preprocess(
         plan.csr_indices = indices if num_edges > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
     plan.sparse_ratio = float(sparse_ratio) if use_csr else 0.0
 
-    # phase 3: nnz-balanced schedule.  A window is split along K only when it alone would exceed ~1/8 of
-    # an SM's share of the TC blocks.
-    cap = max(64, (total_blocks // (_sm_count(dev) * 8)) & ~1)
+    # phase 3: nnz-balanced schedule.  A window is split along K when it alone would exceed ~1/8 of an SM's share of
+    # the TC blocks (load balance), and in any case beyond MAX_CHAIN_BLOCKS (accuracy: the tensor core adds each K-step
+    # into its fp32 accumulator with truncation, a bias that grows linearly with the length of one accumulation chain --
+    # 1.3e-3 relative on a 50 000-step chain of the R-MAT hub rows, measured against an fp64-accumulating oracle; chunks
+    # of <= 1024 K-steps keep it below 4e-5, and the chunks are summed in fp32 round-to-nearest by the fix-up pass).
+    cap = max(64, min(MAX_CHAIN_BLOCKS, (total_blocks // (_sm_count(dev) * 8)) & ~1))
     plan.cap = cap
     max_items, sched_ws_bytes = schedule_sizes(num_nodes, total_blocks, cap)
     sched_ws = alloc_workspace(sched_ws_bytes, dev)
@@ -194,9 +200,11 @@ def spmm(
     row_scale: Optional[torch.Tensor] = None,
     bias: Optional[torch.Tensor] = None,
     relu: bool = False,
+    edge_weights: Optional["EdgeWeights"] = None,
 ):
-    """Reference signature (voltrix/spmm/spmm.py:92-101) plus keyword extensions: ``out`` (caller-owned result) and the
-    fused epilogue ``act(row_scale[:, None] * (A @ feat) + bias)`` (see ``spmm_kernel``)."""
+    """Reference signature (voltrix/spmm/spmm.py:92-101) plus keyword extensions: ``out`` (caller-owned result), the
+    fused epilogue ``act(row_scale[:, None] * (A @ feat) + bias)`` (see ``spmm_kernel``) and ``edge_weights``
+    (``voltrix.edge_weights``): A's stored entries carry values instead of 1 -- on the tensor cores for fp16 / bf16 ``feat``."""
     num_feats = feat.shape[1]
     output = out if out is not None else torch.empty((num_nodes, num_feats), dtype=torch.float32, device=feat.device)
 
@@ -212,9 +220,58 @@ def spmm(
         row_scale=row_scale,
         bias=bias,
         relu=relu,
+        edge_weights=edge_weights,
     )
 
     return output
+
+
+class EdgeWeights:
+    """Per-edge values of a preprocessed matrix, in the two forms the kernels read: fp32 in CSR order (CUDA-core rows) and
+    16-bit value tiles -- one 16 x 8 tile per TC block, built lazily per dense-operand dtype -- for the tensor-core kernel.
+    Build with ``voltrix.edge_weights``; pass to ``voltrix.spmm(..., edge_weights=w)``."""
+
+    def __init__(self, blk_offsets, hind, indptr, indices, values, num_nodes: int, total_blocks: int):
+        self._blk_offsets, self._hind, self._indptr, self._indices = blk_offsets, hind, indptr, indices
+        self.csr_values = values
+        self.num_nodes, self.total_blocks = num_nodes, total_blocks
+        self._tiles = {}
+
+    def tiles(self, dtype) -> torch.Tensor:
+        t = self._tiles.get(dtype)
+        if t is None:
+            dev = self.csr_values.device
+            t = torch.empty(max(self.total_blocks, 1) * BLK_H * BLK_W, dtype=dtype, device=dev)
+            not_found = torch.zeros(1, dtype=torch.int32, device=dev)
+            value_tiles_kernel(self._indptr, self._indices, self.csr_values, self.num_nodes, self._blk_offsets, self._hind,
+                               t[: self.total_blocks * BLK_H * BLK_W], not_found)
+            missing = int(not_found.item())
+            if missing:
+                raise ValueError(f"edge_weights: {missing} stored entries have no slot in the tile format -- the triple was "
+                                 "not built from this CSR matrix")
+            self._tiles[dtype] = t
+        return t
+
+
+def edge_weights(blk_offsets: torch.Tensor, hspa_packed: torch.Tensor, hind: torch.Tensor, indptr: torch.Tensor,
+                 indices: torch.Tensor, values: torch.Tensor) -> EdgeWeights:
+    """Attach a value to every stored entry of the matrix ``csr_preprocess(indptr, indices, ...)`` turned into the triple
+    (no reference counterpart: its format is binary, bmat_kernels.cuh:100-103).  ``values``: ``[nnz]`` in CSR order, any
+    float dtype (kept as fp32; the tensor-core path rounds them to the dense operand's fp16 / bf16 format, the CUDA-core
+    rows use them as fp32).  The matrix must be coalesced (no (row, col) pair stored twice)."""
+    require_cuda()
+    plan = getattr(hspa_packed, "_vx_plan", None)
+    if plan is None:
+        raise ValueError("edge_weights needs the triple returned by voltrix.csr_preprocess (its plan rides on hspa_packed)")
+    if plan.has_duplicates:
+        raise ValueError("edge_weights: the matrix stores a (row, col) pair more than once; coalesce it first")
+    dev = hspa_packed.device
+    indptr = indptr.to(dev, non_blocking=True).contiguous()
+    indices = indices.to(dev, non_blocking=True).contiguous()
+    values = values.to(dev, torch.float32, non_blocking=True).contiguous()
+    assert indptr.dtype == torch.int32 and indices.dtype == torch.int32
+    assert indptr.numel() == plan.num_nodes + 1 and indices.numel() == plan.num_edges == values.numel()
+    return EdgeWeights(blk_offsets, hind, indptr, indices, values, plan.num_nodes, plan.total_blocks)
 
 
 def spmm_weighted(indptr: torch.Tensor, indices: torch.Tensor, values: torch.Tensor, feat: torch.Tensor,
