@@ -41,6 +41,9 @@ extern "C" {
 #define VX_MODEL_CSR_ROWS 1  /* CUDA-core, one warp per CSR row (needs plan CSR) */
 #define VX_MODEL_TILE_ROWS 2 /* CUDA-core, straight from the tile format */
 #define VX_MODEL_TCGEN05_F32 3 /* fp32 input on the tcgen05 path as two bf16 terms (hi + lo); needs plan->split_ws, stages 24 */
+#define VX_MODEL_TCGEN05_F32_AS_F16 4 /* fp32 input rounded to one fp16 term (11 significant bits; the reference rounds to
+                                        * TF32's 10) when every value is inside fp16's normal range -- checked on the device --
+                                        * else model 3's pipeline; needs plan->split_ws, plan->ticket, plan->items, stages 24 */
 
 int vx_abi_version(void);
 
@@ -110,9 +113,10 @@ typedef struct {
   const float *row_scale;      /* [num_nodes] */
   const float *bias;           /* [embedding_dim] */
   int32_t relu;
-  /* ABI v5: 4 bytes of device memory the tensor-core kernel claims its work units from (atomic ticket: persistent CTAs
-   * take the next unit of the LPT list when they finish one).  One per stream that may have a launch in flight; zeroed by
-   * vx_spmm on `stream`.  NULL = static striding over the list. */
+  /* ABI v5: 16 bytes of device memory.  ticket[0]: the counter the tensor-core kernel claims its work units from (atomic
+   * ticket: persistent CTAs take the next unit of the LPT list when they finish one); ticket[1]: the range flag of model 4.
+   * One buffer per stream that may have a launch in flight; zeroed by vx_spmm on `stream`.  NULL = static striding over
+   * the list (and no model 4). */
   int32_t *ticket;
   /* ABI v5: A with a value per stored entry (NULL / NULL = the reference's binary A).  value_tiles: what vx_value_tiles
    * wrote, in `input`'s 16-bit dtype; read by model 0 in place of hspa_packed.  csr_values: fp32 [nnz] in the order of
@@ -123,7 +127,7 @@ typedef struct {
 
 /* `stages` (models 0 and 3) = K-steps of 16 gathered rows kept in flight; it selects a compiled variant, each with its
  * own number of producer warps: 8 (4 warps), 16 (4), 24 (8), 32 (8, the default for any other value), 36 (12), 40 (24),
- * 42 (14).  36 and 42 are the fast ones on large graphs; model 3 needs 24 or less. */
+ * 42 (14).  36 and 42 are the fast ones on large graphs; models 3 and 4 need 24 or less. */
 int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind, int32_t num_nodes,
             int32_t num_edges, int32_t embedding_dim, const void *input, int32_t input_dtype, float *output,
             int32_t model, int32_t stages, const vx_plan_t *plan, void *stream);

@@ -287,3 +287,44 @@ def test_edge_weights_refuses_foreign_triples_and_duplicates():
     st2 = voltrix.csr_preprocess(torch.from_numpy(dup_ptr), torch.from_numpy(dup_idx), 1, num_cols=4)
     with pytest.raises(ValueError, match="more than once"):
         voltrix.edge_weights(*st2, torch.from_numpy(dup_ptr), torch.from_numpy(dup_idx), torch.ones(3))
+
+
+def test_fp32_single_fp16_term_path_and_its_range_fallback():
+    """Model 4: an fp32 operand inside fp16's normal range runs as ONE fp16 term (11 significant bits -- the reference rounds
+    to TF32's 10, spmm_kernels.cuh:1631-1678); one value outside the range flips the device-side flag and the same call takes
+    the two-term bf16 pipeline (16 bits).  Both within the north_star bar; the in-range result equals the fp16 kernel fed the
+    rounded operand bit for bit; the out-of-range result equals model 3's."""
+    import scipy.sparse as sp
+    import voltrix
+    from test_spmm_gpu import _epilogue_case
+    indptr, indices, M = _epilogue_case()
+    N, E = 128, indices.size
+    st = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
+    B = np.random.default_rng(4).standard_normal((M, N)).astype(np.float32)
+    B[np.abs(B) < 1e-3] = 0.25                           # keep every value inside fp16's normal range
+    feat = torch.from_numpy(B).cuda()
+    want = oracle.c().spmm_csr(indptr, indices, B, 0, M, assume_coalesced=True, acc64=True)
+
+    def run(model, x):
+        o = torch.full((M, N), float("nan"), device="cuda")
+        voltrix.spmm_kernel(*st, num_nodes=M, num_edges=E, embedding_dim=N, input=x, output=o, model=model)
+        return o
+
+    got = run(4, feat)
+    assert torch.isfinite(got).all()
+    assert _scaled_err(got.cpu().numpy(), want) <= 5e-4              # 2^-12 relative per operand value
+    assert voltrix.utils.relative_error(got, torch.from_numpy(want).cuda()) <= 1e-2
+    as_f16 = torch.full((M, N), float("nan"), device="cuda")
+    voltrix.spmm_kernel(*st, num_nodes=M, num_edges=E, embedding_dim=N, input=feat.half(), output=as_f16, model=0, stages=42)
+    tc_rows = torch.ones(M, dtype=torch.bool, device="cuda")
+    tc_rows[st[1]._vx_plan.sparse_rows[: st[1]._vx_plan.num_sparse_rows].long()] = False     # sparse rows stay exact fp32
+    assert torch.equal(got[tc_rows], as_f16[tc_rows])
+    # one value fp16 cannot hold: same call, other pipeline
+    feat2 = feat.clone(); feat2[17, 3] = 1.0e6
+    B2 = feat2.cpu().numpy()
+    want2 = oracle.c().spmm_csr(indptr, indices, B2, 0, M, assume_coalesced=True, acc64=True)
+    got2 = run(4, feat2)
+    assert torch.isfinite(got2).all() and _scaled_err(got2.cpu().numpy(), want2) <= 2e-5
+    assert torch.equal(got2, run(3, feat2))
+    # and back: the flag is re-evaluated on every call
+    assert torch.equal(run(4, feat), got)

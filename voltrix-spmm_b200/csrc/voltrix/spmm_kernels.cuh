@@ -11,6 +11,8 @@
 //   model 2  CUDA-core path straight from the tile format (needs nothing but the reference triple).
 //   model 3  fp32 input on the tensor-core path: the operand is split into two bf16 terms (hi + lo, 16 mantissa
 //            bits -- the reference rounds to TF32's 10) in plan.split_ws, both terms accumulate into one TMEM tile.
+//   model 4  fp32 input rounded to ONE fp16 term (11 significant bits, one more than TF32) when every value lies in
+//            fp16's normal range -- decided on the device by the conversion pass -- else model 3's pipeline.
 //
 // Unlike the reference, nothing here throws or calls exit(): errors come back as VX_* codes.
 #ifndef VOLTRIX_B200_SPMM_KERNELS_CUH_
@@ -146,6 +148,40 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
         rc = launch_spmm_tc<__nv_bfloat16, STAGES, NPW, 2>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind,
                                                            num_nodes, b_rows, embedding_dim, terms, output, nullptr,
                                                            stream, plan.epilogue, plan.ticket);
+      }
+      return rc;
+    } else {
+      return VX_ERR_UNSUPPORTED;
+    }
+  } else if (model == 4) {
+    // fp32 input at the reference's precision class, at fp16 cost: the operand is rounded to fp16 (11 significant bits; the
+    // reference rounds to TF32's 10) and runs the one-term tensor-core kernel -- unless a value falls outside fp16's normal
+    // range, which the conversion pass detects; then the gated two-term bf16 pipeline of model 3 runs instead.  Both
+    // pipelines are enqueued, the device flag (plan.ticket[1]) picks one: no host round trip, CUDA-graph capturable.
+    if constexpr (std::is_same<T, float>::value && tc_smem_bytes<STAGES, NPW, 2>() <= 227 * 1024) {
+      if (plan.split_ws == nullptr || plan.ticket == nullptr || plan.items == nullptr) return VX_ERR_INVALID_ARG;
+      if (embedding_dim % 8 != 0) return VX_ERR_UNSUPPORTED;
+      if (plan.num_fixups > 0 && plan.scratch == nullptr) return VX_ERR_INVALID_ARG;
+      int32_t *flag = plan.ticket + 1;
+      __half *as_half = static_cast<__half *>(plan.split_ws);
+      __nv_bfloat16 *terms = static_cast<__nv_bfloat16 *>(plan.split_ws);
+      int rc = launch_cvt_f16(input, as_half, b_rows, embedding_dim, flag, stream);
+      if (rc != VX_OK) return rc;
+      rc = launch_spmm_tc<__half, 42, 14, 1>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
+                                             hspa_packed, hind, num_nodes, b_rows, embedding_dim, as_half, output,
+                                             plan.scratch, stream, plan.epilogue, plan.ticket, flag, 0);
+      if (rc != VX_OK) return rc;
+      rc = launch_split_bf16x2(input, terms, b_rows, embedding_dim, stream, flag, 1);
+      if (rc != VX_OK) return rc;
+      rc = launch_spmm_tc<__nv_bfloat16, STAGES, NPW, 2>(plan.items, plan.num_items, plan.fixups, plan.num_fixups,
+                                                         blks_offsets, hspa_packed, hind, num_nodes, b_rows, embedding_dim,
+                                                         terms, output, plan.scratch, stream, plan.epilogue, plan.ticket,
+                                                         flag, 1);
+      if (rc != VX_OK) return rc;
+      if (plan.num_sparse_rows > 0) {   // sparse windows: exact fp32 rows from the original operand
+        if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows) return VX_ERR_INVALID_ARG;
+        rc = launch_csr_rows<T>(plan.csr_indptr, plan.csr_indices, plan.sparse_rows, plan.num_sparse_rows, embedding_dim,
+                                input, output, stream, -1.f, plan.epilogue);
       }
       return rc;
     } else {

@@ -112,8 +112,12 @@ __global__ void __launch_bounds__(TcGeom<NPW, TERMS>::kThreads, 1)
 vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__restrict__ items, int32_t num_items,
                   int32_t n_feat_tiles, const int32_t *__restrict__ blk_offsets, const uint4 *__restrict__ packed,
                   const int4 *__restrict__ hind4, int32_t num_nodes, int32_t N, float *__restrict__ C,
-                  float *__restrict__ scratch, int32_t term_stride, Epilogue epi, int32_t *__restrict__ ticket) {
+                  float *__restrict__ scratch, int32_t term_stride, Epilogue epi, int32_t *__restrict__ ticket,
+                  const int32_t *__restrict__ gate, int32_t gate_want) {
   using G = TcGeom<NPW, TERMS>;
+  // Optional launch gate (fp32 operands, model 4): two alternative pipelines are enqueued and a flag written by an earlier
+  // kernel on the stream decides which one runs; the other returns here, before it touches a barrier or TMEM.
+  if (gate != nullptr && *gate != gate_want) return;
   static_assert(NPW % G::kKsPerStage == 0, "producer warps must form whole groups");
   static_assert(KSTEPS % G::kKsPerStage == 0 && KSTEPS / G::kKsPerStage > G::kGroups,
                 "the ring must hold more stages than there are producer groups");
@@ -560,7 +564,8 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
                           const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind,
                           int32_t num_nodes, int64_t b_rows,
                           int32_t N, const T *B, float *C, float *scratch, cudaStream_t stream,
-                          const Epilogue &epi = Epilogue(), int32_t *ticket = nullptr) {
+                          const Epilogue &epi = Epilogue(), int32_t *ticket = nullptr, const int32_t *gate = nullptr,
+                          int32_t gate_want = 0) {
   if (num_items <= 0) return VX_OK;
   if (N % 8 != 0 || (reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(hind) & 15) ||
       (reinterpret_cast<uintptr_t>(hspa_packed) & 15))
@@ -584,7 +589,7 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
   kern<<<grid, G::kThreads, smem, stream>>>(tmap, items, num_items, n_feat_tiles, blk_offsets,
                                                  reinterpret_cast<const uint4 *>(hspa_packed),
                                                  reinterpret_cast<const int4 *>(hind), num_nodes, N, C, scratch, N, epi,
-                                                 ticket);
+                                                 ticket, gate, gate_want);
   VX_LAUNCH_CHECK();
   if (num_fixups > 0) {
     vx_spmm_fixup_kernel<<<num_fixups, 256, 0, stream>>>(fixups, num_fixups, scratch, num_nodes, N, C, epi);
@@ -595,7 +600,8 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
 
 // fp32 -> [hi | lo] bf16 terms: out[r, c] = bf16(x), out[r, N + c] = bf16(x - hi).  One thread per 4 values.
 __global__ void vx_spmm_split_bf16x2_kernel(const float4 *__restrict__ in, __nv_bfloat16 *__restrict__ out, int64_t rows,
-                                       int32_t N) {
+                                       int32_t N, const int32_t *__restrict__ gate = nullptr, int32_t gate_want = 0) {
+  if (gate != nullptr && *gate != gate_want) return;
   const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;   // quad index
   const int32_t qpr = N >> 2;
   if (q >= rows * qpr) return;
@@ -616,13 +622,47 @@ __global__ void vx_spmm_split_bf16x2_kernel(const float4 *__restrict__ in, __nv_
   *reinterpret_cast<uint2 *>(o + N) = *reinterpret_cast<const uint2 *>(lo);
 }
 
-inline int launch_split_bf16x2(const float *in, __nv_bfloat16 *out, int64_t rows, int32_t N, cudaStream_t stream) {
+inline int launch_split_bf16x2(const float *in, __nv_bfloat16 *out, int64_t rows, int32_t N, cudaStream_t stream,
+                               const int32_t *gate = nullptr, int32_t gate_want = 0) {
   if (N % 4 != 0 || (reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7))
     return VX_ERR_UNSUPPORTED;
   const int64_t quads = rows * (N >> 2);
   if (quads <= 0) return VX_OK;
   vx_spmm_split_bf16x2_kernel<<<unsigned((quads + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4 *>(in), out,
-                                                                            rows, N);
+                                                                            rows, N, gate, gate_want);
+  VX_LAUNCH_CHECK();
+  return VX_OK;
+}
+
+// fp32 -> fp16 (round to nearest) for the single-term fp32 path (model 4), one thread per 4 values.  fp16 keeps 11
+// significant bits -- one more than the TF32 the reference rounds its operand to (spmm_kernels.cuh:1631-1678) -- as long
+// as the value is inside fp16's normal range.  Any value outside it (|x| > 65504, 0 < |x| < 2^-14, Inf, NaN) raises *flag,
+// which re-routes the whole SpMM to the two-term bf16 pipeline.
+__global__ void vx_spmm_cvt_f16_kernel(const float4 *__restrict__ in, __half *__restrict__ out, int64_t quads,
+                                       int32_t *__restrict__ flag) {
+  const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= quads) return;
+  const float4 v = in[q];
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = fabsf(x[i]);
+    bad |= !(a == 0.f || (a >= 6.103515625e-05f && a <= 65504.f));   // NaN compares false everywhere -> bad
+  }
+  __half2 h[2] = {__floats2half2_rn(x[0], x[1]), __floats2half2_rn(x[2], x[3])};
+  *reinterpret_cast<uint2 *>(out + q * 4) = *reinterpret_cast<const uint2 *>(h);
+  if (bad) *flag = 1;   // benign race: every writer stores the same value
+}
+
+inline int launch_cvt_f16(const float *in, __half *out, int64_t rows, int32_t N, int32_t *flag, cudaStream_t stream) {
+  if (N % 4 != 0 || (reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || flag == nullptr)
+    return VX_ERR_UNSUPPORTED;
+  VX_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int32_t), stream));
+  const int64_t quads = rows * (N >> 2);
+  if (quads <= 0) return VX_OK;
+  vx_spmm_cvt_f16_kernel<<<unsigned((quads + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4 *>(in), out, quads,
+                                                                            flag);
   VX_LAUNCH_CHECK();
   return VX_OK;
 }

@@ -77,6 +77,27 @@ class Runtime:
         self._launch(*self._marshal(values), ctypes.byref(code))
         return code.value
 
+    # -- prepared launches (extension): callers that issue the same launch again and again with only a few pointers
+    # changing marshal the argument list once and patch the changing slots, instead of type-checking and converting
+    # two dozen arguments per call (tens of microseconds of interpreter time -- more than a small SpMM takes on the GPU)
+    def prepare(self, values: Sequence) -> list:
+        """Type-check and marshal ``values`` once; the result goes to ``launch_prepared`` (entries may be replaced by
+        ``ctypes.c_void_p`` / ``ctypes.c_int`` objects in between)."""
+        self._ensure_loaded()
+        return self._marshal(values)
+
+    def arg_index(self, name: str) -> int:
+        self._ensure_loaded()
+        for i, (n, _) in enumerate(self._arg_defs):
+            if n == name:
+                return i
+        raise KeyError(name)
+
+    def launch_prepared(self, cvalues: list) -> int:
+        code = ctypes.c_int(0)
+        self._launch(*cvalues, ctypes.byref(code))
+        return code.value
+
 
 class RuntimeCache:
     """path -> Runtime; a path that is not (yet) a complete artefact maps to None."""

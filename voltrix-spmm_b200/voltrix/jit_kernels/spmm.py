@@ -51,8 +51,10 @@ SPACE_HALF = ({"model": 0, "stages": 36, "npw": 12}, {"model": 0, "stages": 42, 
               {"model": 0, "stages": 40, "npw": 24}, {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
 # variants reachable only through the explicit model=/stages= arguments (tests, scripts): prebuilt as well
 EXTRA_HALF = ({"model": 0, "stages": 16, "npw": 4}, {"model": 0, "stages": 32, "npw": 8})
-# fp32: model 3 = tcgen05 on two bf16 terms (hi + lo); models 1 / 2 = exact-fp32 CUDA-core rows
-SPACE_FP32 = ({"model": 3, "stages": 24, "npw": 8}, {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
+# fp32: model 4 = tcgen05 on ONE fp16 term when the operand is inside fp16's normal range (else model 3's pipeline, decided on
+# the device); model 3 = tcgen05 on two bf16 terms (hi + lo); models 1 / 2 = exact-fp32 CUDA-core rows
+SPACE_FP32 = ({"model": 4, "stages": 24, "npw": 8}, {"model": 3, "stages": 24, "npw": 8}, {"model": 1, "stages": 32, "npw": 8},
+              {"model": 2, "stages": 32, "npw": 8})
 
 
 # A with per-edge values: the WEIGHTED tensor-core instantiations and the weighted CUDA-core CSR rows
@@ -128,12 +130,20 @@ def _ticket(owner, device, stream_id: int) -> torch.Tensor:
 
 
 def fp32_space():
-    """Autotune space for fp32 input.  Model 3 (two bf16 terms on the tensor cores, ~16 mantissa bits) is left out when
-    ``VOLTRIX_FP32_EXACT=1``: then only the exact-fp32 CUDA-core models compete and fp32 results do not depend on which
-    candidate happened to be fastest on this machine."""
+    """Autotune space for fp32 input.  The reference's only arithmetic for fp32 operands is TF32 (10 mantissa bits,
+    spmm_kernels.cuh:1631-1678); here ``VOLTRIX_FP32_MODE`` picks the precision class, so that fp32 numerics follow a stated
+    policy rather than whichever candidate happened to be fastest on this machine:
+      ``tf32``  (default) every candidate: model 4 (one fp16 term, 11 bits, when the operand is in fp16's normal range --
+                else model 3's pipeline), model 3 (two bf16 terms, 16 bits), the exact CUDA-core rows; results carry at
+                least the reference's precision;
+      ``split`` model 3 and the exact rows (>= 16 mantissa bits);
+      ``exact`` (or the older ``VOLTRIX_FP32_EXACT=1``) exact-fp32 CUDA-core rows only."""
     import os
-    if os.environ.get("VOLTRIX_FP32_EXACT", "0") == "1":
-        return tuple(c for c in SPACE_FP32 if c["model"] != 3)
+    mode = os.environ.get("VOLTRIX_FP32_MODE", "exact" if os.environ.get("VOLTRIX_FP32_EXACT", "0") == "1" else "tf32")
+    if mode == "exact":
+        return tuple(c for c in SPACE_FP32 if c["model"] in (1, 2))
+    if mode == "split":
+        return tuple(c for c in SPACE_FP32 if c["model"] != 4)
     return SPACE_FP32
 
 
@@ -174,6 +184,18 @@ def spmm_kernel(
     fused epilogue ``output = act(row_scale[:, None] * (A @ input) + bias[None, :])`` with fp32 ``row_scale [num_nodes]``,
     fp32 ``bias [embedding_dim]`` and ``act`` = ReLU when ``relu`` (all optional, applied in the kernel that writes C), and
     ``edge_weights`` (``voltrix.edge_weights(...)``): A carries a value per stored entry instead of 1."""
+    # Steady state: the same matrix, width, dtype, stream and variant as an earlier call -- replay its marshalled launch
+    # with the operand pointers patched in (see _FastLaunch).
+    stream = current_stream()
+    sid = int(stream.cuda_stream)
+    fast_key = (embedding_dim, input.dtype, sid, model, stages, npw, id(edge_weights) if edge_weights is not None else 0,
+                id(plan) if plan is not None else 0)
+    fast = getattr(hspa_packed, "_vx_fast", None)
+    if fast is not None:
+        hit = fast.get(fast_key)
+        if hit is not None and hit.matches(blk_offsets, hind, num_nodes, num_edges, input, output):
+            check(hit.launch(input, output, row_scale, bias, relu), "spmm_kernel")
+            return
     assert blk_offsets.is_cuda and blk_offsets.dtype == torch.int32
     assert hspa_packed.is_cuda and hspa_packed.dtype == torch.uint32
     assert hind.is_cuda and hind.dtype == torch.int32
@@ -188,8 +210,6 @@ def spmm_kernel(
 
     if plan is None:
         plan = getattr(hspa_packed, "_vx_plan", None)
-    stream = current_stream()
-    sid = int(stream.cuda_stream)
     p = plan.launch_args(embedding_dim, sid) if plan is not None else (None, 0, None, 0, None, None, None, None, 0)
     weighted = edge_weights is not None
     value_tiles = csr_values = None
@@ -201,7 +221,7 @@ def spmm_kernel(
             value_tiles = edge_weights.tiles(input.dtype)
             assert value_tiles.numel() == plan.total_blocks * 128
     if model is not None:   # explicit variant (tests, benchmarks): a space of one, no timing runs
-        stages = int(stages or (24 if int(model) == 3 else 32))
+        stages = int(stages or (24 if int(model) in (3, 4) else 32))
         npw = int(npw or {8: 4, 16: 4, 36: 12, 42: 14, 40: 24}.get(stages, 8))
         space = ({"model": int(model), "stages": stages, "npw": npw},)
         keys = {"ctype": _CTYPE[input.dtype], "fixed": f"{model}/{stages}/{npw}"}
@@ -223,8 +243,8 @@ def spmm_kernel(
     winner = jit_tuner.tuned_keys.get(signature)
     ws_owner = plan if plan is not None else hspa_packed
     split_ws = None
-    if input.dtype == torch.float32 and embedding_dim % 8 == 0 and any(c["model"] == 3 for c in space) and \
-            (winner is None or winner.get("model") == 3):
+    if input.dtype == torch.float32 and embedding_dim % 8 == 0 and any(c["model"] in (3, 4) for c in space) and \
+            (winner is None or winner.get("model") in (3, 4)):
         split_ws = _split_workspace(ws_owner, int(input.shape[0]), embedding_dim, input.device, sid)
     ticket = _ticket(ws_owner, input.device, sid)
     args = (blk_offsets, hspa_packed, hind, num_nodes, num_edges, embedding_dim, input, output, *p,
@@ -241,5 +261,57 @@ def spmm_kernel(
         kernel_tag="spmm",
     )
     check(runtime(*args), "spmm_kernel")
-    if split_ws is not None and jit_tuner.tuned_keys.get(signature, {}).get("model") != 3:
+    if split_ws is not None and jit_tuner.tuned_keys.get(signature, {}).get("model") not in (3, 4):
         getattr(ws_owner, "_vx_split_ws", {}).clear()
+        split_ws = None
+        args = args[:ARG_SPLIT_WS] + (None,) + args[ARG_SPLIT_WS + 1:]
+    try:
+        if fast is None:
+            fast = hspa_packed._vx_fast = {}
+        fast[fast_key] = _FastLaunch(runtime, args, blk_offsets, hind, num_nodes, num_edges, input, output)
+    except AttributeError:      # a tensor subclass that refuses attributes: every call takes the full path
+        pass
+
+
+_ARG_NAMES = tuple(n for n, _ in arg_defs_for(torch.float16))
+ARG_INPUT, ARG_OUTPUT, ARG_SPLIT_WS = _ARG_NAMES.index("input"), _ARG_NAMES.index("output"), _ARG_NAMES.index("split_ws")
+ARG_ROW_SCALE, ARG_BIAS, ARG_RELU = _ARG_NAMES.index("row_scale"), _ARG_NAMES.index("bias"), _ARG_NAMES.index("relu")
+
+
+class _FastLaunch:
+    """One fully resolved SpMM launch (variant chosen, plan / scratch / ticket pointers marshalled): later calls with the
+    same matrix, width, dtype and stream patch five slots -- input, output, row_scale, bias, relu -- and go straight to the
+    artefact's ``launch``.  The tensors whose pointers are baked in are kept alive here."""
+
+    def __init__(self, runtime, args, blk_offsets, hind, num_nodes, num_edges, input, output):
+        import ctypes
+        self._c = ctypes
+        self.runtime = runtime
+        self.keep = args
+        self.cvals = runtime.prepare(args)
+        self.ids = (blk_offsets.data_ptr(), hind.data_ptr(), num_nodes, num_edges)
+        self.in_shape, self.out_shape = tuple(input.shape), tuple(output.shape)
+
+    def matches(self, blk_offsets, hind, num_nodes, num_edges, input, output) -> bool:
+        return (self.ids == (blk_offsets.data_ptr(), hind.data_ptr(), num_nodes, num_edges)
+                and tuple(input.shape) == self.in_shape and tuple(output.shape) == self.out_shape
+                and input.is_cuda and output.is_cuda and output.dtype == torch.float32
+                and input.is_contiguous() and output.is_contiguous())
+
+    def launch(self, input, output, row_scale, bias, relu) -> int:
+        vp = self._c.c_void_p
+        cv = list(self.cvals)      # private copy: two Python threads may launch the same matrix
+        cv[ARG_INPUT] = vp(input.data_ptr())
+        cv[ARG_OUTPUT] = vp(output.data_ptr())
+        if row_scale is not None:
+            assert row_scale.is_cuda and row_scale.dtype == torch.float32 and row_scale.numel() == self.out_shape[0]
+            cv[ARG_ROW_SCALE] = vp(row_scale.data_ptr())
+        else:
+            cv[ARG_ROW_SCALE] = vp(None)
+        if bias is not None:
+            assert bias.is_cuda and bias.dtype == torch.float32 and bias.numel() == self.out_shape[1]
+            cv[ARG_BIAS] = vp(bias.data_ptr())
+        else:
+            cv[ARG_BIAS] = vp(None)
+        cv[ARG_RELU] = self._c.c_int(1 if relu else 0)
+        return self.runtime.launch_prepared(cv)
