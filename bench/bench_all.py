@@ -2,8 +2,9 @@
 graph_gen.py, run each method as a subprocess, parse its `[X] ... time: ` line, append results.csv
 (`Method,Dataset,FeatDim,Reorder,Time (ms)`).  Differences: graphs are the synthetic suite of
 voltrix.graphs.named_suite(); the N sweep is 32/64/128/256/512 (BASELINE.json configs[2]); methods are the ones
-that exist on this box -- cuSPARSE and Voltrix (fp32 / fp16); the competitor wrappers (Sputnik, RoDe, DTC-SpMM,
-GE-SpMM, TC-GNN) need third-party builds that are out of scope."""
+that exist on this box -- cuSPARSE and Voltrix (fp32 / fp16), plus the competitors bench/competitors/build.py compiled
+for sm_100a from the reference's own sources into bench/_competitors/ (GE-SpMM, TC-GNN, RoDe, Sputnik; fp32, like the
+reference's columns).  DTC-SpMM is not built (torch extension on top of cmake builds of glog and Sputnik)."""
 import argparse
 import csv
 import os
@@ -17,6 +18,15 @@ METHODS = {
     "Voltrix": ([sys.executable, os.path.join(HERE, "bm_voltrix.py")], "[Voltrix] time: "),
     "Voltrix-fp16": ([sys.executable, os.path.join(HERE, "bm_voltrix.py"), "--dtype", "fp16"], "[Voltrix] time: "),
 }
+COMP = os.path.join(HERE, "_competitors")
+RODE_DIMS = (32, 128, 256, 512, 1024)       # one eval binary per feature width (patches/rode_fix.patch adds 256-1024)
+if os.path.exists(os.path.join(COMP, "gespmm")):
+    METHODS["GE-SPMM"] = ([os.path.join(COMP, "gespmm")], "[GE-SPMM] Embedding time: ")
+if os.path.exists(os.path.join(COMP, "tcgnn")):
+    METHODS["TC-GNN"] = ([os.path.join(COMP, "tcgnn")], "[TC-GNN] Kernel time: ")
+if os.path.isdir(os.path.join(COMP, "rode", "build", "eval")):
+    METHODS["RoDe"] = ([sys.executable, os.path.join(HERE, "bm_rode.py")], "[RoDe] Elapsed time: ")
+    METHODS["Sputnik"] = ([sys.executable, os.path.join(HERE, "bm_sputnik.py")], "[Sputnik] Elapsed time: ")
 FEATURE_DIMS = [32, 64, 128, 256, 512]
 
 
@@ -33,6 +43,7 @@ def main():
     ap.add_argument("--feature_dims", nargs="*", type=int, default=FEATURE_DIMS)
     ap.add_argument("--results", default="results.csv")
     ap.add_argument("--reorder", action="store_true", help="also run the reordered variants")
+    ap.add_argument("--no_competitors", action="store_true", help="only cuSPARSE and Voltrix")
     args = ap.parse_args()
     sys.path.insert(0, os.path.join(HERE, "..", "voltrix-spmm_b200"))
     from voltrix.graphs import named_suite
@@ -46,14 +57,28 @@ def main():
             for fd in args.feature_dims:
                 for reorder in ([False, True] if args.reorder else [False]):
                     with tempfile.TemporaryDirectory() as tmp:
+                        need_mtx = "RoDe" in METHODS and fd in RODE_DIMS and not args.no_competitors
                         gen = [sys.executable, os.path.join(HERE, "graph_gen.py"), "--data_name", ds, "--num_feats",
-                               str(fd), "--mtx_max_nnz", "0"] + (["--reorder"] if reorder else [])
+                               str(fd), "--mtx_max_nnz", "20000000" if need_mtx else "0"] + (["--reorder"] if reorder else [])
                         r = subprocess.run(gen, cwd=tmp, capture_output=True, text=True)
                         if r.returncode != 0:
                             print(f"graph_gen failed for {ds}: {r.stderr[-300:]}")
                             continue
                         for method, (cmd, marker) in METHODS.items():
-                            r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
+                            competitor = method in ("GE-SPMM", "TC-GNN", "RoDe", "Sputnik")
+                            if competitor and (args.no_competitors or reorder):     # the reference runs them un-reordered
+                                continue
+                            if method in ("RoDe", "Sputnik"):
+                                if fd not in RODE_DIMS or not os.path.exists(os.path.join(tmp, "data.mtx")):
+                                    continue
+                                cmd = cmd + ["--feat_dim", str(fd)]
+                            if method in ("GE-SPMM", "TC-GNN") and fd % 128 != 0:   # their kernels tile 128 features per warp
+                                continue
+                            try:
+                                r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, timeout=600)
+                            except subprocess.TimeoutExpired:
+                                print(f"{method:14s} {ds:14s} N={fd:4d}: TIMEOUT")
+                                continue
                             t = parse_time(r.stdout, marker)
                             print(f"{method:14s} {ds:14s} N={fd:4d} reorder={reorder}: "
                                   f"{t if t is not None else 'FAILED ' + r.stderr[-200:]}")
