@@ -319,8 +319,13 @@ def test_fp32_single_fp16_term_path_and_its_range_fallback():
     tc_rows = torch.ones(M, dtype=torch.bool, device="cuda")
     tc_rows[st[1]._vx_plan.sparse_rows[: st[1]._vx_plan.num_sparse_rows].long()] = False     # sparse rows stay exact fp32
     assert torch.equal(got[tc_rows], as_f16[tc_rows])
-    # one value fp16 cannot hold: same call, other pipeline
-    feat2 = feat.clone(); feat2[17, 3] = 1.0e6
+    # the carrier is scaled by a power of two first: an operand that is tiny (or huge) as a whole is still one fp16 term
+    for k in (2.0 ** -40, 2.0 ** 30):
+        got_k = run(4, feat * k)
+        assert _scaled_err(got_k.cpu().numpy(), want * np.float32(k)) <= 5e-4
+        assert torch.equal(got_k[tc_rows], (got * k)[tc_rows])             # power-of-two scaling is exact end to end
+    # a dynamic range fp16 cannot span (2^-14 .. 2^15 after scaling): same call, other pipeline
+    feat2 = feat.clone(); feat2[17, 3] = 1.0e9
     B2 = feat2.cpu().numpy()
     want2 = oracle.c().spmm_csr(indptr, indices, B2, 0, M, assume_coalesced=True, acc64=True)
     got2 = run(4, feat2)

@@ -63,3 +63,68 @@ def test_lsh_reorder_recovers_planted_communities():
     # degree ordering alone does not find the structure
     after_deg = reorder.tc_block_count(*reorder.permute_graph(indptr, indices, reorder.degree_reorder(indptr)))
     assert after < after_deg
+
+
+def test_cluster_reorder_against_the_restated_tca_algorithm():
+    """voltrix.reorder.cluster_reorder beside oracle/tca_reorder.py -- the CPU restatement of
+    third-party/DTC-SpMM/reordering/TCA_reorder.py the reference's published numbers were relabelled with (it cannot run
+    here: datasketch / cugraph / cudf / libMHCUDA are absent) -- on planted-partition graphs with shuffled labels.  The
+    quantity compared is what the reordering is for: the number of 16x8 TC blocks (= gathered B rows / 8)."""
+    from oracle.tca_reorder import tca_reorder
+    from voltrix import reorder
+    from voltrix.graphs import planted_partition_csr
+    for M, community, p_in, p_out, slack in ((2048, 64, 0.3, 0.0005, 1.2), (2048, 32, 0.5, 0.001, 1.2),
+                                             (4096, 128, 0.15, 0.0002, 1.0)):
+        indptr, indices = planted_partition_csr(M, community, p_in, p_out, seed=1)
+        before = reorder.tc_block_count(indptr, indices)
+        perm = reorder.cluster_reorder(indptr, indices)
+        assert torch.equal(torch.sort(perm).values, torch.arange(M))
+        assert torch.equal(perm, reorder.cluster_reorder(indptr, indices)), "deterministic"
+        ours = reorder.tc_block_count(*reorder.permute_graph(indptr, indices, perm))
+        lsh = reorder.tc_block_count(*reorder.permute_graph(indptr, indices, reorder.lsh_reorder(indptr, indices)))
+        tca_perm = torch.from_numpy(tca_reorder(indptr.numpy(), indices.numpy()))
+        tca = reorder.tc_block_count(*reorder.permute_graph(indptr, indices, tca_perm))
+        assert ours <= lsh, (ours, lsh)
+        assert ours <= slack * tca, (M, community, before, ours, tca)
+        assert ours * 1.6 <= before, (before, ours)
+
+
+def test_tca_oracle_restatement_basics():
+    """The restatement itself: a valid permutation; rows with identical neighbour sets end up adjacent; a cluster never
+    exceeds the window height before level 2 concatenates clusters."""
+    from oracle.tca_reorder import _greedy_cluster, tca_reorder
+    rng = np.random.default_rng(0)
+    groups = [sorted(rng.choice(400, 12, replace=False).tolist()) for _ in range(6)]
+    owner = rng.permutation(np.repeat(np.arange(6), 8))          # 48 rows, 8 per group, shuffled
+    indptr = np.arange(49, dtype=np.int32) * 12
+    indices = np.concatenate([groups[g] for g in owner]).astype(np.int32)
+    perm = tca_reorder(indptr, indices)
+    assert sorted(perm.tolist()) == list(range(48))
+    labels = owner[perm]
+    assert (np.diff(labels) != 0).sum() == 5, "six groups of identical rows must come out as six contiguous runs"
+    clusters = _greedy_cluster([set(indices[indptr[i]:indptr[i + 1]].tolist()) for i in range(48)], 0.2, 4)
+    assert max(len(c) for c in clusters) <= 2 * 4 - 1       # closed once it REACHES the cap (TCA_reorder.py:186-189)
+
+
+@pytest.mark.gpu
+def test_reorder_on_the_gpu_keeps_the_product_and_cuts_blocks():
+    """Both reorderings on the device: the relabelled SpMM gives the original product (rows permuted back), the tile count
+    drops, and the tensor-core SpMM gets faster data (fewer TC blocks) -- checked through the plan."""
+    import voltrix
+    from voltrix import reorder
+    from voltrix.graphs import planted_partition_csr
+    M, N = 32_768, 64
+    indptr, indices = planted_partition_csr(M, 128, 0.15, 0.0002, seed=3, device="cuda")
+    E = indices.numel()
+    feat = torch.randn(M, N, device="cuda").half()
+    st = voltrix.csr_preprocess(indptr, indices, M)
+    want = voltrix.spmm(*st, M, E, feat)
+    for fn in (reorder.lsh_reorder, reorder.cluster_reorder):
+        perm = fn(indptr, indices)
+        assert perm.is_cuda and torch.equal(torch.sort(perm).values, torch.arange(M, device="cuda"))
+        ip2, ix2 = reorder.permute_graph(indptr, indices, perm)
+        st2 = voltrix.csr_preprocess(ip2, ix2, M)
+        assert st2[1]._vx_plan.total_blocks == reorder.tc_block_count(ip2, ix2)
+        assert st2[1]._vx_plan.total_blocks * 1.5 <= st[1]._vx_plan.total_blocks
+        got = reorder.unpermute_rows(voltrix.spmm(*st2, M, E, reorder.permute_rows(feat, perm)), perm)
+        assert (got - want).abs().max().item() / want.abs().max().item() <= 1e-5      # same sums, different order

@@ -72,7 +72,21 @@ struct Epilogue {
   const float *row_scale = nullptr;   // [num_nodes]
   const float *bias = nullptr;        // [embedding_dim]
   int32_t relu = 0;
-  __host__ __device__ bool any() const { return row_scale != nullptr || bias != nullptr || relu != 0; }
+  // model 4 (fp32 operand carried as one fp16 term): the operand was pre-multiplied by 2^s, s = 14 - floor(log2(max |x|)),
+  // so that its largest value sits just below fp16's maximum; the accumulator is multiplied back by 2^-s here (exact).
+  // Points at the bit pattern of max |x| written by the range pass; null everywhere else.
+  const int32_t *pow2_max_bits = nullptr;
+  __host__ __device__ bool any() const {
+    return row_scale != nullptr || bias != nullptr || relu != 0 || pow2_max_bits != nullptr;
+  }
+  // 2^s of the fp16 carrier from the bit pattern of max |x| (0 -> no scaling; |s| is capped by the range pass)
+  __device__ static __forceinline__ int carrier_shift(int32_t max_bits) {
+    return max_bits == 0 ? 0 : 14 - (((max_bits >> 23) & 0xff) - 127);
+  }
+  __device__ __forceinline__ float pre_scale() const {
+    if (pow2_max_bits == nullptr) return 1.f;
+    return __int_as_float((127 - carrier_shift(__ldg(pow2_max_bits))) << 23);   // 2^-s
+  }
   __device__ __forceinline__ float scale_of(int64_t row) const { return row_scale ? __ldg(row_scale + row) : 1.f; }
   __device__ __forceinline__ float bias_of(int32_t f) const { return bias ? __ldg(bias + f) : 0.f; }
   __device__ __forceinline__ float apply(float acc, float s, float b) const {

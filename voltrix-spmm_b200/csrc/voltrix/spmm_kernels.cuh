@@ -162,14 +162,16 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
       if (plan.split_ws == nullptr || plan.ticket == nullptr || plan.items == nullptr) return VX_ERR_INVALID_ARG;
       if (embedding_dim % 8 != 0) return VX_ERR_UNSUPPORTED;
       if (plan.num_fixups > 0 && plan.scratch == nullptr) return VX_ERR_INVALID_ARG;
-      int32_t *flag = plan.ticket + 1;
+      int32_t *flag = plan.ticket + 1;       // ticket[1..3]: flag, bits of max |x|, bits of min non-zero |x|
       __half *as_half = static_cast<__half *>(plan.split_ws);
       __nv_bfloat16 *terms = static_cast<__nv_bfloat16 *>(plan.split_ws);
       int rc = launch_cvt_f16(input, as_half, b_rows, embedding_dim, flag, stream);
       if (rc != VX_OK) return rc;
+      Epilogue carried = plan.epilogue;      // the fp16 carrier is 2^s times the operand: scale the accumulator back
+      carried.pow2_max_bits = flag + 1;
       rc = launch_spmm_tc<__half, 42, 14, 1>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
                                              hspa_packed, hind, num_nodes, b_rows, embedding_dim, as_half, output,
-                                             plan.scratch, stream, plan.epilogue, plan.ticket, flag, 0);
+                                             plan.scratch, stream, carried, plan.ticket, flag, 0);
       if (rc != VX_OK) return rc;
       rc = launch_split_bf16x2(input, terms, b_rows, embedding_dim, stream, flag, 1);
       if (rc != VX_OK) return rc;

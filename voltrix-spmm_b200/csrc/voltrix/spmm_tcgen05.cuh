@@ -469,11 +469,11 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
           dst = C + int64_t(it.window) * BLK_H * N + f;
           nrows = min(BLK_H, num_nodes - it.window * BLK_H);   // partial tail window: rows >= M do not exist
           if (epi.any()) {   // fused epilogue; K-split partial tiles (slot >= 0) get it in the fix-up pass instead
-            const float bf = epi.bias_of(f);
+            const float bf = epi.bias_of(f), pre = epi.pre_scale();
 #pragma unroll
             for (int r = 0; r < BLK_H; ++r)
               if (r < nrows)
-                v[r] = __float_as_uint(epi.apply(__uint_as_float(v[r]), epi.scale_of(int64_t(it.window) * BLK_H + r), bf));
+                v[r] = __float_as_uint(epi.apply(__uint_as_float(v[r]), epi.scale_of(int64_t(it.window) * BLK_H + r) * pre, bf));
           }
         } else {
           dst = scratch + int64_t(it.slot) * BLK_H * N + f;
@@ -493,16 +493,19 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
 // Sums the partial tiles of K-split windows in slot order (fixed order => deterministic).
 __global__ void vx_spmm_fixup_kernel(const FixupItem *__restrict__ fixups, int32_t num_fixups,
                                 const float *__restrict__ scratch, int32_t num_nodes, int32_t N,
-                                float *__restrict__ C, Epilogue epi) {
+                                float *__restrict__ C, Epilogue epi, const int32_t *__restrict__ gate = nullptr,
+                                int32_t gate_want = 0) {
+  if (gate != nullptr && *gate != gate_want) return;
   const int32_t i = blockIdx.x;
   if (i >= num_fixups) return;
+  const float pre = epi.pre_scale();
   const FixupItem fx = fixups[i];
   const int32_t nrows = min(BLK_H, num_nodes - fx.window * BLK_H);
   const int32_t elems = nrows * N;   // rows of a slot are laid out [16][N]
   for (int32_t e = threadIdx.x; e < elems; e += blockDim.x) {
     float s = 0.f;
     for (int32_t k = 0; k < fx.slot_count; ++k) s += scratch[int64_t(fx.slot_begin + k) * BLK_H * N + e];
-    if (epi.any()) s = epi.apply(s, epi.scale_of(int64_t(fx.window) * BLK_H + e / N), epi.bias_of(e % N));
+    if (epi.any()) s = epi.apply(s, epi.scale_of(int64_t(fx.window) * BLK_H + e / N) * pre, epi.bias_of(e % N));
     C[int64_t(fx.window) * BLK_H * N + e] = s;
   }
 }
@@ -592,7 +595,7 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
                                                  ticket, gate, gate_want);
   VX_LAUNCH_CHECK();
   if (num_fixups > 0) {
-    vx_spmm_fixup_kernel<<<num_fixups, 256, 0, stream>>>(fixups, num_fixups, scratch, num_nodes, N, C, epi);
+    vx_spmm_fixup_kernel<<<num_fixups, 256, 0, stream>>>(fixups, num_fixups, scratch, num_nodes, N, C, epi, gate, gate_want);
     VX_LAUNCH_CHECK();
   }
   return VX_OK;
@@ -634,35 +637,71 @@ inline int launch_split_bf16x2(const float *in, __nv_bfloat16 *out, int64_t rows
   return VX_OK;
 }
 
-// fp32 -> fp16 (round to nearest) for the single-term fp32 path (model 4), one thread per 4 values.  fp16 keeps 11
-// significant bits -- one more than the TF32 the reference rounds its operand to (spmm_kernels.cuh:1631-1678) -- as long
-// as the value is inside fp16's normal range.  Any value outside it (|x| > 65504, 0 < |x| < 2^-14, Inf, NaN) raises *flag,
-// which re-routes the whole SpMM to the two-term bf16 pipeline.
-__global__ void vx_spmm_cvt_f16_kernel(const float4 *__restrict__ in, __half *__restrict__ out, int64_t quads,
-                                       int32_t *__restrict__ flag) {
-  const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (q >= quads) return;
-  const float4 v = in[q];
-  const float x[4] = {v.x, v.y, v.z, v.w};
-  bool bad = false;
+// ---- model 4: an fp32 operand carried as ONE fp16 term -------------------------------------------------------------------
+// fp16 keeps 11 significant bits -- one more than the TF32 the reference rounds its operand to (spmm_kernels.cuh:1631-1678)
+// -- for values inside its normal range, 2^-14 .. 65504.  The operand is therefore scaled by a power of two (exact) that
+// puts its largest magnitude just under fp16's maximum, which leaves 2^29 of dynamic range below it; the accumulator is
+// scaled back in the epilogue.  Two passes over the operand, both on the stream, no host round trip:
+//   range pass    max |x|, min non-zero |x| (atomics on the bit patterns), non-finite values
+//   convert pass  x * 2^s -> fp16; raises `flag` if the range pass saw Inf / NaN or min |x| * 2^s < 2^-14 (an operand
+//                 spanning more than fp16's normal range) -- then the gated two-term bf16 pipeline runs instead.
+// state[0] = flag, state[1] = bits of max |x|, state[2] = bits of min non-zero |x|.
+__global__ void vx_spmm_absrange_kernel(const float4 *__restrict__ in, int64_t quads, int32_t *__restrict__ state) {
+  uint32_t mx = 0u, mn = 0x7f7fffffu;
+  bool nonfinite = false;
+  for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < quads; q += int64_t(gridDim.x) * blockDim.x) {
+    const float4 v = in[q];
+    const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float a = fabsf(x[i]);
-    bad |= !(a == 0.f || (a >= 6.103515625e-05f && a <= 65504.f));   // NaN compares false everywhere -> bad
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t a = __float_as_uint(x[i]) & 0x7fffffffu;
+      nonfinite |= a >= 0x7f800000u;
+      mx = max(mx, a);
+      if (a != 0u) mn = min(mn, a);
+    }
   }
-  __half2 h[2] = {__floats2half2_rn(x[0], x[1]), __floats2half2_rn(x[2], x[3])};
-  *reinterpret_cast<uint2 *>(out + q * 4) = *reinterpret_cast<const uint2 *>(h);
-  if (bad) *flag = 1;   // benign race: every writer stores the same value
+  for (int off = 16; off > 0; off >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+  }
+  nonfinite = __any_sync(0xffffffffu, nonfinite);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<unsigned int *>(state + 1), mx);
+    atomicMin(reinterpret_cast<unsigned int *>(state + 2), mn);
+    if (nonfinite) state[0] = 1;
+  }
 }
 
-inline int launch_cvt_f16(const float *in, __half *out, int64_t rows, int32_t N, int32_t *flag, cudaStream_t stream) {
-  if (N % 4 != 0 || (reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || flag == nullptr)
+__global__ void vx_spmm_cvt_f16_kernel(const float4 *__restrict__ in, __half *__restrict__ out, int64_t quads,
+                                       int32_t *__restrict__ state) {
+  const int32_t max_bits = state[1], min_bits = state[2];
+  const int s = Epilogue::carrier_shift(max_bits);
+  // representable: |s| small enough for 2^s to be a normal float, and the smallest value still normal in fp16 after scaling
+  const int min_exp = ((min_bits >> 23) & 0xff) - 127;
+  const bool ok = state[0] == 0 && s > -100 && s < 100 && (max_bits == 0 || min_exp + s >= -14);
+  const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q == 0 && !ok) state[0] = 1;
+  if (!ok || q >= quads) return;      // the other pipeline will run: nothing to convert
+  const float k = __int_as_float((127 + s) << 23);   // 2^s
+  const float4 v = in[q];
+  __half2 h[2] = {__floats2half2_rn(v.x * k, v.y * k), __floats2half2_rn(v.z * k, v.w * k)};
+  *reinterpret_cast<uint2 *>(out + q * 4) = *reinterpret_cast<const uint2 *>(h);
+}
+
+// state: 3 ints of device memory (flag, max bits, min bits), initialised here
+inline int launch_cvt_f16(const float *in, __half *out, int64_t rows, int32_t N, int32_t *state, cudaStream_t stream) {
+  if (N % 4 != 0 || (reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || state == nullptr)
     return VX_ERR_UNSUPPORTED;
-  VX_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int32_t), stream));
+  VX_CUDA_TRY(cudaMemsetAsync(state, 0, 2 * sizeof(int32_t), stream));      // flag = 0, max |x| = 0
+  VX_CUDA_TRY(cudaMemsetAsync(state + 2, 0x7f, sizeof(int32_t), stream));   // min |x| = 0x7f7f7f7f (a huge finite float)
   const int64_t quads = rows * (N >> 2);
   if (quads <= 0) return VX_OK;
+  const int64_t want_ctas = (quads + 255) / 256, cap_ctas = int64_t(device_sm_count()) * 16;
+  const int grid = int(want_ctas < cap_ctas ? want_ctas : cap_ctas);
+  vx_spmm_absrange_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4 *>(in), quads, state);
+  VX_LAUNCH_CHECK();
   vx_spmm_cvt_f16_kernel<<<unsigned((quads + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4 *>(in), out, quads,
-                                                                            flag);
+                                                                            state);
   VX_LAUNCH_CHECK();
   return VX_OK;
 }
