@@ -12,7 +12,8 @@ datasets (and no network) here, so `--data_name` selects a synthetic graph of th
 voltrix.graphs (`reddit`, `ddi`, `products`, `rmat<scale>`, `uniform:<M>:<nnz>` ...).  If
 `<base_folder>/<data_name>.npz` does exist it is loaded (keys `src_li`/`dst_li`/`num_nodes`, the TC-GNN layout).
 `--seed` is honoured (the reference parses it and ignores it).  `--reorder` relabels the nodes with
-voltrix.reorder.lsh_reorder (min-hash LSH on the GPU -- the role DTC-SpMM's offline TCA_reorder.py plays for the reference).
+voltrix.reorder.cluster_reorder (window-aware agglomerative clustering on the GPU -- the role DTC-SpMM's offline
+TCA_reorder.py plays for the reference).
 """
 import argparse
 import os
@@ -47,7 +48,7 @@ def load_graph(args, device):
         ip, ix = graphs.suite_graph(name, seed=args.seed, device=device)
     if args.reorder:
         from voltrix import reorder
-        ip, ix = reorder.permute_graph(ip, ix, reorder.lsh_reorder(ip, ix, seed=args.seed))
+        ip, ix = reorder.permute_graph(ip, ix, reorder.cluster_reorder(ip, ix, seed=args.seed))
     return ip, ix
 
 

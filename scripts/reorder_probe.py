@@ -1,4 +1,4 @@
-"""Measured effect of voltrix.reorder.lsh_reorder on a graph with planted communities and shuffled labels:
+"""Measured effect of voltrix.reorder.lsh_reorder / cluster_reorder on a graph with planted communities and shuffled labels:
 TC blocks and SpMM time before / after relabelling, result checked through the inverse permutation."""
 import os
 import sys
@@ -35,16 +35,21 @@ def timeit(fn, iters=7):
 st = voltrix.csr_preprocess(indptr, indices, M)
 t0 = timeit(lambda: voltrix.spmm(*st, M, nnz, feat))
 base = voltrix.spmm(*st, M, nnz, feat)
-torch.cuda.synchronize(); t = time.perf_counter()
-perm = reorder.lsh_reorder(indptr, indices)
-ip2, ix2 = reorder.permute_graph(indptr, indices, perm)
-torch.cuda.synchronize(); t_re = time.perf_counter() - t
-st2 = voltrix.csr_preprocess(ip2, ix2, M)
-feat2 = reorder.permute_rows(feat, perm)
-t1 = timeit(lambda: voltrix.spmm(*st2, M, nnz, feat2))
-got = reorder.unpermute_rows(voltrix.spmm(*st2, M, nnz, feat2), perm)
-err = ((got - base).abs().max() / base.abs().max()).item()
 print(f"planted partition M={M} nnz={nnz} N={N} fp16")
 print(f"shuffled labels : TCB={st[1]._vx_plan.total_blocks:9d}  spmm {t0:.3f} ms")
-print(f"lsh_reorder     : TCB={st2[1]._vx_plan.total_blocks:9d}  spmm {t1:.3f} ms  ({t0 / t1:.2f}x)  reorder+relabel {t_re * 1e3:.0f} ms  "
-      f"max scaled diff after un-permuting {err:.1e}")
+for name, fn in (("lsh_reorder", reorder.lsh_reorder), ("cluster_reorder", reorder.cluster_reorder)):
+    torch.cuda.synchronize(); t = time.perf_counter()
+    perm = fn(indptr, indices)
+    ip2, ix2 = reorder.permute_graph(indptr, indices, perm)
+    torch.cuda.synchronize(); t_re = time.perf_counter() - t
+    st2 = voltrix.csr_preprocess(ip2, ix2, M)
+    feat2 = reorder.permute_rows(feat, perm)
+    t1 = timeit(lambda: voltrix.spmm(*st2, M, nnz, feat2))
+    got = reorder.unpermute_rows(voltrix.spmm(*st2, M, nnz, feat2), perm)
+    err = ((got - base).abs().max() / base.abs().max()).item()
+    print(f"{name:16s}: TCB={st2[1]._vx_plan.total_blocks:9d}  spmm {t1:.3f} ms  ({t0 / t1:.2f}x)  reorder+relabel {t_re * 1e3:.0f} ms  "
+          f"max scaled diff after un-permuting {err:.1e}")
+ip0, ix0 = planted_partition_csr(M, community=256, p_in=0.2, p_out=2e-6, seed=0, device=dev, shuffle=False)
+st0 = voltrix.csr_preprocess(ip0, ix0, M)
+t_ideal = timeit(lambda: voltrix.spmm(*st0, M, ix0.numel(), feat))
+print(f"unshuffled graph: TCB={st0[1]._vx_plan.total_blocks:9d}  spmm {t_ideal:.3f} ms  (the order the generator planted)")

@@ -125,6 +125,6 @@ def test_reorder_on_the_gpu_keeps_the_product_and_cuts_blocks():
         ip2, ix2 = reorder.permute_graph(indptr, indices, perm)
         st2 = voltrix.csr_preprocess(ip2, ix2, M)
         assert st2[1]._vx_plan.total_blocks == reorder.tc_block_count(ip2, ix2)
-        assert st2[1]._vx_plan.total_blocks * 1.5 <= st[1]._vx_plan.total_blocks
+        assert st2[1]._vx_plan.total_blocks * 1.2 <= st[1]._vx_plan.total_blocks
         got = reorder.unpermute_rows(voltrix.spmm(*st2, M, E, reorder.permute_rows(feat, perm)), perm)
         assert (got - want).abs().max().item() / want.abs().max().item() <= 1e-5      # same sums, different order

@@ -160,7 +160,9 @@ def test_properties_at_scale(dtype):
     fy = voltrix.spmm(blk, packed, hind, M, E, Y)
     fxy = voltrix.spmm(blk, packed, hind, M, E, (X.float() + Y.float()).to(dtype))
     scale = fxy.abs().max().item()
-    tol = 2e-2 if dtype == torch.float16 else 1e-4      # fp16: X+Y is rounded to fp16 once more
+    # fp16: X+Y is rounded to fp16 once more.  fp32: the default precision class is the reference's (TF32-like: the
+    # operand may travel as one fp16 term, 2^-12 relative per value); VOLTRIX_FP32_MODE=split / exact tighten it (below)
+    tol = 2e-2 if dtype == torch.float16 else 2e-3
     assert (fxy - (fx + fy)).abs().max().item() / scale < tol
     # independent paths agree (tensor-core vs CSR rows vs tile rows)
     ref = None
@@ -174,7 +176,16 @@ def test_properties_at_scale(dtype):
     # against cuSPARSE fp32 (the reference's comparison, tests/test_spmm.py:75-85)
     sparse = torch.sparse_csr_tensor(indptr, indices, torch.ones(E, device="cuda"), size=(M, M))
     base = sparse @ X.float()
-    assert (fx - base).abs().max().item() / scale < 1e-4
+    assert (fx - base).abs().max().item() / scale < (1e-4 if dtype == torch.float16 else 1e-3)
+    if dtype == torch.float32:      # the tighter precision classes, selected by policy (not by which candidate was fastest)
+        import os
+        for mode, bar in (("split", 2e-5), ("exact", 1e-5)):
+            os.environ["VOLTRIX_FP32_MODE"] = mode
+            try:
+                got = voltrix.spmm(blk, packed, hind, M, E, X)
+            finally:
+                os.environ.pop("VOLTRIX_FP32_MODE", None)
+            assert (got - base).abs().max().item() / scale < bar, mode
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -414,3 +425,30 @@ def test_weighted_csr_spmm(dtype, density, N):
     got2 = voltrix.spmm_weighted(ip, ix, vals, feat, row_scale=scale, bias=bias, relu=True).cpu().numpy()
     want2 = np.maximum(want * scale.cpu().numpy()[:, None] + bias.cpu().numpy()[None, :], 0.0)
     assert _scaled_err(got2, want2) <= 2e-5
+
+
+def test_reference_timing_hook_agrees_with_cuda_events():
+    """The reference's timing call -- GPU_bench(fn, kernel_name="spmm") (bench/bm_voltrix.py:36, utils.py:232-303): profiler
+    time of the kernels whose name contains "spmm", L2 flushed per iteration -- must give the per-call kernel time: every
+    kernel an SpMM launches carries "spmm" in its name, and the figure agrees with CUDA events around the same calls."""
+    import voltrix
+    from voltrix.graphs import chung_lu_csr
+    from voltrix.utils import GPU_bench
+    M, N = 100_000, 128
+    indptr, indices = chung_lu_csr(M, avg_degree=60, max_degree=30_000, seed=6, device="cuda")   # hub windows: K-split + fix-up
+    E = indices.numel()
+    st = voltrix.csr_preprocess(indptr, indices, M)
+    assert st[1]._vx_plan.num_fixups >= 1
+    feat = torch.rand(M, N, device="cuda").half()
+    fn = lambda: voltrix.spmm(*st, M, E, feat)   # noqa: E731
+    fn(); torch.cuda.synchronize()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    events_ms = float(np.median(ts))
+    hook_ms = GPU_bench(fn, iters=10, warmup=10, kernel_name="spmm")
+    assert 0.6 * events_ms <= hook_ms <= 1.1 * events_ms, (hook_ms, events_ms)   # kernel time <= event time (launch gaps)

@@ -129,6 +129,11 @@ def _ticket(owner, device, stream_id: int) -> torch.Tensor:
     return buf
 
 
+def fp32_mode() -> str:
+    import os
+    return os.environ.get("VOLTRIX_FP32_MODE", "exact" if os.environ.get("VOLTRIX_FP32_EXACT", "0") == "1" else "tf32")
+
+
 def fp32_space():
     """Autotune space for fp32 input.  The reference's only arithmetic for fp32 operands is TF32 (10 mantissa bits,
     spmm_kernels.cuh:1631-1678); here ``VOLTRIX_FP32_MODE`` picks the precision class, so that fp32 numerics follow a stated
@@ -138,8 +143,7 @@ def fp32_space():
                 least the reference's precision;
       ``split`` model 3 and the exact rows (>= 16 mantissa bits);
       ``exact`` (or the older ``VOLTRIX_FP32_EXACT=1``) exact-fp32 CUDA-core rows only."""
-    import os
-    mode = os.environ.get("VOLTRIX_FP32_MODE", "exact" if os.environ.get("VOLTRIX_FP32_EXACT", "0") == "1" else "tf32")
+    mode = fp32_mode()
     if mode == "exact":
         return tuple(c for c in SPACE_FP32 if c["model"] in (1, 2))
     if mode == "split":
@@ -189,7 +193,7 @@ def spmm_kernel(
     stream = current_stream()
     sid = int(stream.cuda_stream)
     fast_key = (embedding_dim, input.dtype, sid, model, stages, npw, id(edge_weights) if edge_weights is not None else 0,
-                id(plan) if plan is not None else 0)
+                id(plan) if plan is not None else 0, fp32_mode() if input.dtype == torch.float32 else "")
     fast = getattr(hspa_packed, "_vx_fast", None)
     if fast is not None:
         hit = fast.get(fast_key)
@@ -236,6 +240,8 @@ def spmm_kernel(
         keys = {"ctype": _CTYPE[input.dtype], "feature_hash": feature_hash(hspa_packed), "N": embedding_dim, "plan": caps}
 
     keys["weighted"] = "true" if weighted else "false"
+    if input.dtype == torch.float32 and model is None:
+        keys["fp32"] = fp32_mode()      # winners are per precision class
 
     # fp32 on the tensor cores (model 3) needs a bf16 [rows, 2N] workspace: hand it over while that model is still a
     # candidate for this key, drop it once the tuner has settled on a CUDA-core model

@@ -89,9 +89,11 @@ def bench_kineto(fn, kernel_names: Union[str, Tuple[str, ...]], num_tests: int =
     out = []
     for name in names:
         total_us = sum(e.device_time_total for e in events if name in e.key)
+        # number of fn() calls the profiler actually recorded = launches of the kernel every call launches (the one with
+        # the highest count); dividing by num_tests instead over-counts whenever the warm-up batch is traced as well
         calls = max((e.count for e in events if name in e.key), default=0)
         assert calls > 0, f"no profiled kernel matches '{name}'"
-        out.append(total_us / num_tests / 1e6)
+        out.append(total_us / calls / 1e6)
     if trace_path is not None:
         prof.export_chrome_trace(trace_path)
     return tuple(out) if is_tupled else out[0]
