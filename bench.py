@@ -53,6 +53,9 @@ def make_workload(name: str, device, scale: float):
     if name == "c1":
         indptr, indices = graphs.uniform_csr(16384, 1_000_000, seed=0, device=device)
         return indptr, indices, 64, "uniform 16384^2, 1M nnz, N=64 fp16"
+    if name in {n for n, _, _ in graphs.named_suite()}:      # C3 shapes (scripts/ only; the bench CLI does not list them)
+        indptr, indices = graphs.suite_graph(name, seed=0, device=device)
+        return indptr, indices, 128, f"{name}-shaped Chung-Lu (C3 suite), N=128 fp16"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -368,6 +371,21 @@ def parity_check(indptr_h, indices_h, row0, feat, out_rows, budget_nnz: int, nco
                       "operand"}
 
 
+def host_link_floor(world: int, h2d_bytes: int, d2h_bytes: int):
+    """What the host<->device links of this pool's boxes allow for the end-to-end leg (measured, profiles/host_links.json):
+    the larger of the two directions at the aggregate bandwidth k concurrently copying GPUs reach with both directions busy."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "host_links.json")) as f:
+            db = json.load(f)
+        bw = db["both"].get(str(world))
+        if bw is None:
+            return None
+        ms = max(h2d_bytes, d2h_bytes) / (bw * 2**30) * 1e3
+        return {"ms_per_step": ms, "aggregate_gib_s_per_direction": bw, "source": db["source"]}
+    except Exception:
+        return None
+
+
 def committed_floors(workload: str, scale: float, world: int, ms: float):
     """Measured floors of the tensor-core kernel (timing-only builds) from the committed report, if it covers this run."""
     try:
@@ -543,6 +561,7 @@ def measure(workload: str, args, world: int, rank: int, dev, headline: bool, ste
                "api": "voltrix.HostStreamedSpMM.submit(pinned B, pinned C) every step: H2D of B (1/world row slice per rank "
                       "+ NCCL all-gather over NVLink when world > 1), voltrix.spmm, D2H of this rank's rows of C; the three "
                       "legs of consecutive steps overlap on three streams"}
+        e2e["host_link_floor"] = host_link_floor(world, int(M * N * 2), int(M * N * 4))
         if e2e_serial_ms is not None:
             e2e["serial_ms_per_step"] = e2e_serial_ms
             e2e["serial_value"] = flops / e2e_serial_ms / 1e6

@@ -92,7 +92,8 @@ struct VecAccess {
   __device__ static void store(float *dst, const float (&acc)[N]) {
     float4 *d = reinterpret_cast<float4 *>(dst);
 #pragma unroll
-    for (int i = 0; i < N / 4; ++i) d[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    // streaming stores: C is written once and never read by this kernel -- keep L2 for the gathered B rows
+    for (int i = 0; i < N / 4; ++i) __stcs(d + i, make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]));
   }
 };
 template <typename T>
@@ -224,7 +225,7 @@ vx_spmm_csr_subwarp_rows_kernel(const int32_t *__restrict__ indptr, const int32_
   }
   float4 *dst = reinterpret_cast<float4 *>(C + int64_t(row) * N + f0);
 #pragma unroll
-  for (int i = 0; i < EPL / 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+  for (int i = 0; i < EPL / 4; ++i) __stcs(dst + i, make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]));
 }
 
 // One warp per row of the tile format.  Lane l scans TC block (b0 + l) of the row's window for

@@ -75,6 +75,33 @@ def shard_csr(indptr: torch.Tensor, indices: torch.Tensor, r0: int, r1: int) -> 
     return (indptr[r0:r1 + 1] - lo).to(torch.int32).contiguous(), indices[lo:hi].contiguous()
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off (``/sys/bus/pci/devices/<bus id>/numa_node``),
+    so that pinned host buffers allocated afterwards (first touch) live next to the GPU's PCIe root: host<->device copies of
+    the end-to-end path then do not cross the socket interconnect.  Returns the node, or None when the topology is not
+    exposed (single-socket hosts, containers without sysfs)."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, AttributeError, ValueError, RuntimeError, AssertionError):
+        return None
+
+
 def operand_slices(rows: int, world: int) -> Tuple[int, List[Tuple[int, int]]]:
     """Equal row slices of the dense operand for the per-step exchange: ``chunk = ceil(rows / world)`` rows per rank (what
     an all-gather needs), the last ranks' slices clipped to ``rows`` (possibly empty).  Returns ``(chunk, [(lo, hi)])``."""

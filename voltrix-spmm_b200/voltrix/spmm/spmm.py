@@ -41,7 +41,7 @@ BLK_W = 8
 # SPARSE_RATIO x the rows the tensor-core path would gather for it (16 per K-step).
 DEFAULT_SPARSE_RATIO = 0.5
 # Longest run of TC blocks one work item accumulates in the tensor core before its partial tile is handed to the fix-up pass.
-MAX_CHAIN_BLOCKS = 2048
+MAX_CHAIN_BLOCKS = 4096
 
 
 class SpmmPlan:
@@ -161,8 +161,10 @@ def csr_preprocess(
     # phase 3: nnz-balanced schedule.  A window is split along K when it alone would exceed ~1/8 of an SM's share of
     # the TC blocks (load balance), and in any case beyond MAX_CHAIN_BLOCKS (accuracy: the tensor core adds each K-step
     # into its fp32 accumulator with truncation, a bias that grows linearly with the length of one accumulation chain --
-    # 1.3e-3 relative on a 50 000-step chain of the R-MAT hub rows, measured against an fp64-accumulating oracle; chunks
-    # of <= 1024 K-steps keep it below 4e-5, and the chunks are summed in fp32 round-to-nearest by the fix-up pass).
+    # 1.3e-3 relative on a 50 000-step chain of the R-MAT hub rows, measured against an fp64-accumulating oracle (1.3e-5
+    # with 1024-step chains); chunks of <= 2048 K-steps keep it below ~6e-5, and the chunks are summed in fp32
+    # round-to-nearest by the fix-up pass.  4096 blocks is above the largest window of the Reddit-shaped graph, whose
+    # shards therefore need no fix-up launch).
     cap = max(64, min(MAX_CHAIN_BLOCKS, (total_blocks // (_sm_count(dev) * 8)) & ~1))
     plan.cap = cap
     max_items, sched_ws_bytes = schedule_sizes(num_nodes, total_blocks, cap)
