@@ -158,14 +158,15 @@ def csr_preprocess(
         plan.csr_indices = indices if num_edges > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
     plan.sparse_ratio = float(sparse_ratio) if use_csr else 0.0
 
-    # phase 3: nnz-balanced schedule.  A window is split along K when it alone would exceed ~1/8 of an SM's share of
-    # the TC blocks (load balance), and in any case beyond MAX_CHAIN_BLOCKS (accuracy: the tensor core adds each K-step
+    # phase 3: nnz-balanced schedule.  A window is split along K when it alone would exceed ~1/3 of an SM's share of
+    # the TC blocks (load balance: units are claimed dynamically in LPT order, so an item that size, started first, never
+    # forms the tail), and in any case beyond MAX_CHAIN_BLOCKS (accuracy: the tensor core adds each K-step
     # into its fp32 accumulator with truncation, a bias that grows linearly with the length of one accumulation chain --
     # 1.3e-3 relative on a 50 000-step chain of the R-MAT hub rows, measured against an fp64-accumulating oracle (1.3e-5
     # with 1024-step chains); chunks of <= 2048 K-steps keep it below ~6e-5, and the chunks are summed in fp32
     # round-to-nearest by the fix-up pass.  4096 blocks is above the largest window of the Reddit-shaped graph, whose
     # shards therefore need no fix-up launch).
-    cap = max(64, min(MAX_CHAIN_BLOCKS, (total_blocks // (_sm_count(dev) * 8)) & ~1))
+    cap = max(64, min(MAX_CHAIN_BLOCKS, (total_blocks // (_sm_count(dev) * 3)) & ~1))
     plan.cap = cap
     max_items, sched_ws_bytes = schedule_sizes(num_nodes, total_blocks, cap)
     sched_ws = alloc_workspace(sched_ws_bytes, dev)
