@@ -83,10 +83,11 @@ typedef struct { int32_t num_items, num_slots, num_fixups, num_sparse_rows; } vx
 
 int64_t vx_schedule_max_items(int32_t num_nodes, int64_t total_blocks, int32_t cap);
 size_t vx_schedule_workspace_bytes(int32_t num_nodes, int64_t max_items);
-/* phase 1: classify windows (sparse_ratio <= 0 or indptr == NULL: all tensor-core), split windows with
- * more than `cap` blocks; fills fixups[<=W], sparse_rows[<=num_nodes], counts (device). */
+/* phase 1: classify windows (indptr == NULL: all tensor-core; else a window goes to the CUDA-core rows when its nnz is
+ * below sparse_ratio x the rows its TC blocks gather, or when it has at most small_blocks TC blocks and any padding at all),
+ * split windows with more than `cap` blocks; fills fixups[<=W], sparse_rows[<=num_nodes], counts (device). */
 int vx_schedule_build(const int32_t *pointer1, const int32_t *indptr, int32_t num_nodes, int32_t cap,
-                      float sparse_ratio, int64_t max_items, vx_fixup_item_t *fixups, int32_t *sparse_rows,
+                      float sparse_ratio, int32_t small_blocks, int64_t max_items, vx_fixup_item_t *fixups, int32_t *sparse_rows,
                       vx_schedule_counts_t *counts, void *workspace, size_t workspace_bytes, void *stream);
 /* phase 2 (after reading counts back): items[num_items] in LPT order. */
 int vx_schedule_sort(int32_t num_items, int32_t num_nodes, int64_t max_items, vx_work_item_t *items,
@@ -123,6 +124,7 @@ typedef struct {
    * csr_indices; read by model 1 and by model 0's CUDA-core rows for sparse windows. */
   const void *value_tiles;
   const float *csr_values;
+  float sparse_mean_degree;    /* non-zeros per row over sparse_rows; <= 0 = unknown (warp-per-row kernel) */
 } vx_plan_t;
 
 /* `stages` (models 0 and 3) = K-steps of 16 gathered rows kept in flight; it selects a compiled variant, each with its

@@ -22,6 +22,7 @@ ap.add_argument("--dtype", default="fp16")
 ap.add_argument("--only", default=None)
 ap.add_argument("--once", action="store_true")
 ap.add_argument("--sparse_ratio", type=float, default=None)
+ap.add_argument("--small_blocks", type=int, default=None)
 ap.add_argument("--N", type=int, default=None)
 args = ap.parse_args()
 
@@ -32,6 +33,8 @@ if args.N:
 M, nnz = indptr.numel() - 1, indices.numel()
 dt = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
 kw = {} if args.sparse_ratio is None else {"sparse_ratio": args.sparse_ratio}
+if args.small_blocks is not None:
+    kw["small_blocks"] = args.small_blocks
 blk, packed, hind = voltrix.csr_preprocess(indptr, indices, M, **kw)
 plan = packed._vx_plan
 print(f"{desc}: M={M} nnz={nnz} N={N} TCB={plan.total_blocks} items={plan.num_items} sparse_rows={plan.num_sparse_rows} "

@@ -339,7 +339,7 @@ def test_c_abi_plan_with_epilogue():
                     ("csr_indices", ctypes.c_void_p), ("sparse_rows", ctypes.c_void_p), ("num_sparse_rows", ctypes.c_int32),
                     ("input_rows", ctypes.c_int64), ("split_ws", ctypes.c_void_p), ("row_scale", ctypes.c_void_p),
                     ("bias", ctypes.c_void_p), ("relu", ctypes.c_int32), ("ticket", ctypes.c_void_p),
-                    ("value_tiles", ctypes.c_void_p), ("csr_values", ctypes.c_void_p)]
+                    ("value_tiles", ctypes.c_void_p), ("csr_values", ctypes.c_void_p), ("sparse_mean_degree", ctypes.c_float)]
 
     indptr, indices, M = _epilogue_case()
     N = 128
@@ -351,7 +351,7 @@ def test_c_abi_plan_with_epilogue():
     scratch = p.scratch(N)
     plan = Plan(p.items.data_ptr(), p.num_items, p.fixups.data_ptr(), p.num_fixups, scratch.data_ptr() if scratch is not None else None,
                 p.csr_indptr.data_ptr(), p.csr_indices.data_ptr(), p.sparse_rows.data_ptr(), p.num_sparse_rows, M, None,
-                scale.data_ptr(), bias.data_ptr(), 1, None, None, None)
+                scale.data_ptr(), bias.data_ptr(), 1, None, None, None, 0.0)
     vp, i32 = ctypes.c_void_p, ctypes.c_int32
     lib.vx_spmm.restype = ctypes.c_int
     lib.vx_spmm.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, vp, i32, i32, ctypes.POINTER(Plan), vp]

@@ -102,9 +102,10 @@ size_t vx_schedule_workspace_bytes(int32_t num_nodes, int64_t max_items) {
 }
 
 int vx_schedule_build(const int32_t *pointer1, const int32_t *indptr, int32_t num_nodes, int32_t cap,
-                      float sparse_ratio, int64_t max_items, vx_fixup_item_t *fixups, int32_t *sparse_rows,
+                      float sparse_ratio, int32_t small_blocks, int64_t max_items, vx_fixup_item_t *fixups,
+                      int32_t *sparse_rows,
                       vx_schedule_counts_t *counts, void *workspace, size_t workspace_bytes, void *stream) {
-  return build_schedule(pointer1, indptr, num_nodes, cap, sparse_ratio, max_items,
+  return build_schedule(pointer1, indptr, num_nodes, cap, sparse_ratio, small_blocks, max_items,
                         reinterpret_cast<FixupItem *>(fixups), sparse_rows,
                         reinterpret_cast<ScheduleCounts *>(counts), workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -137,6 +138,7 @@ int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32
     p.ticket = plan->ticket;
     p.value_tiles = plan->value_tiles;
     p.csr_values = plan->csr_values;
+    p.sparse_mean_degree = plan->sparse_mean_degree > 0.f ? plan->sparse_mean_degree : -1.f;
   }
   cudaStream_t s = (cudaStream_t)stream;
   switch (input_dtype) {

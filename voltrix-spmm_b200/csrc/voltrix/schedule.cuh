@@ -75,7 +75,7 @@ inline int carve_schedule_workspace(void *ws, size_t bytes, int32_t W, int64_t m
 
 // pass 1: classify + count.  indptr may be null (no CSR available) -> every window is tensor-core.
 __global__ void vx_sched_count_kernel(const int32_t *__restrict__ pointer1, const int32_t *__restrict__ indptr,
-                                      int32_t num_nodes, int32_t W, int32_t cap, float sparse_ratio,
+                                      int32_t num_nodes, int32_t W, int32_t cap, float sparse_ratio, int32_t small_blocks,
                                       int32_t *__restrict__ n_items, int32_t *__restrict__ n_slots,
                                       int32_t *__restrict__ n_fix, int32_t *__restrict__ n_rows) {
   int32_t w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,11 +84,13 @@ __global__ void vx_sched_count_kernel(const int32_t *__restrict__ pointer1, cons
   if (w < W) {
     int32_t cnt = pointer1[w + 1] - pointer1[w];
     bool sparse = false;
-    if (indptr != nullptr && sparse_ratio > 0.f) {
+    if (indptr != nullptr && (sparse_ratio > 0.f || small_blocks > 0)) {
       int32_t r0 = w * BLK_H, r1 = min(r0 + BLK_H, num_nodes);
       int32_t nnz = indptr[r1] - indptr[r0];
       int32_t tc_rows = 16 * ((cnt + 1) >> 1);   // B rows the tensor-core path gathers (K = 16 per step)
-      sparse = float(nnz) < sparse_ratio * float(tc_rows);
+      // small windows (at most `small_blocks` TC blocks) pay a whole work unit -- claim, metadata, pipeline fill, TMEM
+      // epilogue -- for one or two K-steps: they go to the CUDA-core rows as soon as ANY gathered slot would be padding
+      sparse = float(nnz) < sparse_ratio * float(tc_rows) || (cnt <= small_blocks && nnz < tc_rows);
       if (sparse) rows = r1 - r0;
     }
     if (!sparse) {
@@ -136,7 +138,7 @@ __global__ void vx_sched_fill_kernel(const int32_t *__restrict__ pointer1, int32
 // First phase, on `stream`: classify, count, emit.  Outputs (device): unsorted items in the workspace,
 // fixups[W], sparse_rows[num_nodes], counts.  The caller reads `counts` back, then calls sort_schedule.
 inline int build_schedule(const int32_t *pointer1, const int32_t *indptr /*nullable*/, int32_t num_nodes, int32_t cap,
-                          float sparse_ratio, int64_t max_items, FixupItem *fixups,
+                          float sparse_ratio, int32_t small_blocks, int64_t max_items, FixupItem *fixups,
                           int32_t *sparse_rows, ScheduleCounts *counts, void *workspace, size_t workspace_bytes,
                           cudaStream_t stream) {
   int32_t W = ceil_div<int32_t>(num_nodes, BLK_H);
@@ -146,7 +148,7 @@ inline int build_schedule(const int32_t *pointer1, const int32_t *indptr /*nulla
   int rc = carve_schedule_workspace(workspace, workspace_bytes, W, max_items, ws);
   if (rc != VX_OK) return rc;
   int threads = 256, grid = ceil_div(W + 1, threads);
-  vx_sched_count_kernel<<<grid, threads, 0, stream>>>(pointer1, indptr, num_nodes, W, cap, sparse_ratio, ws.n_items,
+  vx_sched_count_kernel<<<grid, threads, 0, stream>>>(pointer1, indptr, num_nodes, W, cap, sparse_ratio, small_blocks, ws.n_items,
                                                       ws.n_slots, ws.n_fix, ws.n_rows);
   VX_LAUNCH_CHECK();
   int32_t *arrs[4] = {ws.n_items, ws.n_slots, ws.n_fix, ws.n_rows};

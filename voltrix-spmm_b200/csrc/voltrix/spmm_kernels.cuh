@@ -37,6 +37,7 @@ struct SpmmPlan {
   const int32_t *csr_indices = nullptr;
   const int32_t *sparse_rows = nullptr;  // rows of the windows routed to the CUDA-core path
   int32_t num_sparse_rows = 0;
+  float sparse_mean_degree = -1.f;       // non-zeros per row over sparse_rows (< 0 = unknown): picks warp- vs group-per-row
   int64_t input_rows = 0;                // rows of the dense operand (0 = num_nodes, i.e. square A);
                                          // differs for a row shard of A, whose columns span the full matrix
   void *split_ws = nullptr;              // model 3: bf16 [input_rows][2 * embedding_dim] workspace
@@ -70,7 +71,9 @@ inline int voltrix_spmm_weighted_forward_cuda(const int32_t *blks_offsets, const
       if (rc != VX_OK) return rc;
       if (plan.num_sparse_rows > 0) {
         if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows || !plan.csr_values) return VX_ERR_INVALID_ARG;
-        rc = launch_csr_rows_weighted<T>(plan.csr_indptr, plan.csr_indices, plan.csr_values, plan.num_sparse_rows, -1,
+        const int64_t sparse_nnz = plan.sparse_mean_degree >= 0.f
+                                       ? int64_t(plan.sparse_mean_degree * float(plan.num_sparse_rows)) : int64_t(-1);
+        rc = launch_csr_rows_weighted<T>(plan.csr_indptr, plan.csr_indices, plan.csr_values, plan.num_sparse_rows, sparse_nnz,
                                          embedding_dim, input, output, stream, plan.epilogue, plan.sparse_rows);
       }
       return rc;
@@ -108,7 +111,7 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
         if (plan.num_sparse_rows > 0) {
           if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows) return VX_ERR_INVALID_ARG;
           rc = launch_csr_rows<T>(plan.csr_indptr, plan.csr_indices, plan.sparse_rows, plan.num_sparse_rows,
-                                  embedding_dim, input, output, stream, -1.f, plan.epilogue);
+                                  embedding_dim, input, output, stream, plan.sparse_mean_degree, plan.epilogue);
         }
       } else {
         rc = launch_spmm_tc<T, STAGES, NPW>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind, num_nodes, b_rows,
@@ -142,7 +145,7 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
         if (plan.num_sparse_rows > 0) {   // sparse windows: exact fp32 rows from the original operand
           if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows) return VX_ERR_INVALID_ARG;
           rc = launch_csr_rows<T>(plan.csr_indptr, plan.csr_indices, plan.sparse_rows, plan.num_sparse_rows,
-                                  embedding_dim, input, output, stream, -1.f, plan.epilogue);
+                                  embedding_dim, input, output, stream, plan.sparse_mean_degree, plan.epilogue);
         }
       } else {
         rc = launch_spmm_tc<__nv_bfloat16, STAGES, NPW, 2>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind,
@@ -183,7 +186,7 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
       if (plan.num_sparse_rows > 0) {   // sparse windows: exact fp32 rows from the original operand
         if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows) return VX_ERR_INVALID_ARG;
         rc = launch_csr_rows<T>(plan.csr_indptr, plan.csr_indices, plan.sparse_rows, plan.num_sparse_rows, embedding_dim,
-                                input, output, stream, -1.f, plan.epilogue);
+                                input, output, stream, plan.sparse_mean_degree, plan.epilogue);
       }
       return rc;
     } else {

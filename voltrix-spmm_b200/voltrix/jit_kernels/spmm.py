@@ -31,6 +31,7 @@ plan.csr_indptr = csr_indptr;
 plan.csr_indices = csr_indices;
 plan.sparse_rows = sparse_rows;
 plan.num_sparse_rows = num_sparse_rows;
+plan.sparse_mean_degree = sparse_mean_degree;
 plan.input_rows = input_rows;
 plan.split_ws = split_ws;
 plan.epilogue.row_scale = row_scale;
@@ -81,6 +82,7 @@ def arg_defs_for(dtype):
         ("csr_indices", torch.int32),
         ("sparse_rows", torch.int32),
         ("num_sparse_rows", int),
+        ("sparse_mean_degree", float),
         ("input_rows", int),
         ("split_ws", torch.bfloat16),
         ("row_scale", torch.float32),
@@ -214,7 +216,7 @@ def spmm_kernel(
 
     if plan is None:
         plan = getattr(hspa_packed, "_vx_plan", None)
-    p = plan.launch_args(embedding_dim, sid) if plan is not None else (None, 0, None, 0, None, None, None, None, 0)
+    p = plan.launch_args(embedding_dim, sid) if plan is not None else (None, 0, None, 0, None, None, None, None, 0, -1.0)
     weighted = edge_weights is not None
     value_tiles = csr_values = None
     if weighted:

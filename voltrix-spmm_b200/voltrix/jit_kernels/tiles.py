@@ -85,7 +85,7 @@ sizes[0] = max_items;
 sizes[1] = (int64_t)voltrix::schedule_workspace_bytes(W, max_items);
 if (op == 0) { __return_code = 0; return; }
 if (op == 1) {
-  __return_code = voltrix::build_schedule(pointer1, indptr, num_nodes, cap, sparse_ratio, max_items,
+  __return_code = voltrix::build_schedule(pointer1, indptr, num_nodes, cap, sparse_ratio, small_blocks, max_items,
                                           reinterpret_cast<voltrix::FixupItem*>(fixups), sparse_rows,
                                           reinterpret_cast<voltrix::ScheduleCounts*>(counts), workspace,
                                           (size_t)workspace_units * 256, stream);
@@ -102,6 +102,7 @@ _sched_arg_defs = (
     ("total_blocks", int),
     ("cap", int),
     ("sparse_ratio", float),
+    ("small_blocks", int),
     ("num_items", int),
     ("items", torch.int),
     ("fixups", torch.int),
@@ -122,22 +123,22 @@ def _sched_runtime(args):
 def schedule_sizes(num_nodes: int, total_blocks: int, cap: int):
     """-> (max_items, workspace_bytes)"""
     sizes = torch.zeros(2, dtype=torch.int64)
-    args = (0, None, None, num_nodes, total_blocks, cap, 0.0, 0, None, None, None, None, None, 0, sizes,
+    args = (0, None, None, num_nodes, total_blocks, cap, 0.0, 0, 0, None, None, None, None, None, 0, sizes,
             current_stream())
     check(_sched_runtime(args)(*args), "schedule_kernel (size query)")
     return int(sizes[0]), int(sizes[1])
 
 
 def schedule_build_kernel(pointer1, indptr, num_nodes: int, total_blocks: int, cap: int, sparse_ratio: float, fixups,
-                          sparse_rows, counts, workspace):
+                          sparse_rows, counts, workspace, small_blocks: int = 0):
     sizes = torch.zeros(2, dtype=torch.int64)
-    args = (1, pointer1, indptr, num_nodes, total_blocks, cap, float(sparse_ratio), 0, None, fixups, sparse_rows,
+    args = (1, pointer1, indptr, num_nodes, total_blocks, cap, float(sparse_ratio), int(small_blocks), 0, None, fixups, sparse_rows,
             counts, workspace, workspace.numel() // 256, sizes, current_stream())
     check(_sched_runtime(args)(*args), "schedule_build_kernel")
 
 
 def schedule_sort_kernel(num_items: int, num_nodes: int, total_blocks: int, cap: int, items, workspace):
     sizes = torch.zeros(2, dtype=torch.int64)
-    args = (2, None, None, num_nodes, total_blocks, cap, 0.0, num_items, items, None, None, None, workspace,
+    args = (2, None, None, num_nodes, total_blocks, cap, 0.0, 0, num_items, items, None, None, None, workspace,
             workspace.numel() // 256, sizes, current_stream())
     check(_sched_runtime(args)(*args), "schedule_sort_kernel")

@@ -40,6 +40,8 @@ BLK_W = 8
 # A window goes to the CUDA-core row path when gathering its nnz rows one by one moves fewer than
 # SPARSE_RATIO x the rows the tensor-core path would gather for it (16 per K-step).
 DEFAULT_SPARSE_RATIO = 0.5
+# Windows of at most this many TC blocks go to the CUDA-core rows whenever they contain any padding (see schedule.cuh).
+DEFAULT_SMALL_BLOCKS = 8
 # Longest run of TC blocks one work item accumulates in the tensor core before its partial tile is handed to the fix-up pass.
 MAX_CHAIN_BLOCKS = 4096
 
@@ -54,6 +56,8 @@ class SpmmPlan:
         self.unique_nnz = 0
         self.cap = 0
         self.sparse_ratio = 0.0
+        self.small_blocks = 0
+        self.sparse_mean_degree = -1.0   # non-zeros per CUDA-core row (picks the warp- or the group-per-row kernel)
         self.items: Optional[torch.Tensor] = None        # int32 [num_items, 4]  (window, blk_begin, blk_count, slot)
         self.fixups: Optional[torch.Tensor] = None       # int32 [num_fixups, 4] (window, slot_begin, slot_count, 0)
         self.sparse_rows: Optional[torch.Tensor] = None  # int32 [num_sparse_rows]
@@ -88,7 +92,8 @@ class SpmmPlan:
         """The plan part of the spmm ``launch`` argument list (see jit_kernels/spmm.py::arg_defs_for)."""
         return (self.items, self.num_items, self.fixups if self.num_fixups else None, self.num_fixups,
                 self.scratch(embedding_dim, stream_id), self.csr_indptr, self.csr_indices,
-                self.sparse_rows if self.num_sparse_rows else None, self.num_sparse_rows)
+                self.sparse_rows if self.num_sparse_rows else None, self.num_sparse_rows,
+                float(self.sparse_mean_degree))
 
 
 def _sm_count(device) -> int:
@@ -102,6 +107,7 @@ def csr_preprocess(
     sparse_ratio: float = DEFAULT_SPARSE_RATIO,
     keep_csr: bool = True,
     num_cols: Optional[int] = None,
+    small_blocks: Optional[int] = None,
 ):
     """``num_cols`` (extension): number of columns of A when it is not square -- a row shard of a larger
     matrix has ``num_nodes`` rows but columns spanning the whole graph."""
@@ -173,14 +179,19 @@ def csr_preprocess(
     fixups = torch.empty((max(num_row_windows, 1), 4), dtype=torch.int32, device=dev)
     sparse_rows = torch.empty(max(num_nodes, 1), dtype=torch.int32, device=dev)
     counts = torch.zeros(4, dtype=torch.int32, device=dev)
-    schedule_build_kernel(pointer1, plan.csr_indptr if plan.sparse_ratio > 0 else None, num_nodes, total_blocks, cap,
-                          plan.sparse_ratio, fixups, sparse_rows, counts, sched_ws)
+    plan.small_blocks = int(DEFAULT_SMALL_BLOCKS if small_blocks is None else small_blocks) if use_csr else 0
+    routing = plan.sparse_ratio > 0 or plan.small_blocks > 0
+    schedule_build_kernel(pointer1, plan.csr_indptr if routing else None, num_nodes, total_blocks, cap,
+                          plan.sparse_ratio, fixups, sparse_rows, counts, sched_ws, small_blocks=plan.small_blocks)
     plan.num_items, plan.num_slots, plan.num_fixups, plan.num_sparse_rows = (int(v) for v in counts.tolist())
     items = torch.empty((max(plan.num_items, 1), 4), dtype=torch.int32, device=dev)
     schedule_sort_kernel(plan.num_items, num_nodes, total_blocks, cap, items, sched_ws)
     plan.items = items
     plan.fixups = fixups[: max(plan.num_fixups, 1)].clone()
     plan.sparse_rows = sparse_rows[: max(plan.num_sparse_rows, 1)].clone()
+    if plan.num_sparse_rows > 0:
+        rows = plan.sparse_rows[: plan.num_sparse_rows].long()
+        plan.sparse_mean_degree = float((indptr[rows + 1] - indptr[rows]).sum().item()) / plan.num_sparse_rows
     torch.cuda.current_stream().synchronize()
     del sched_ws
 
@@ -400,7 +411,7 @@ class HostStreamedSpMM:
 FORMAT_VERSION = 1
 _PLAN_TENSORS = ("items", "fixups", "sparse_rows", "csr_indptr", "csr_indices", "block_partition")
 _PLAN_SCALARS = ("num_nodes", "num_edges", "total_blocks", "unique_nnz", "cap", "sparse_ratio", "num_items", "num_slots",
-                 "num_fixups", "num_sparse_rows")
+                 "num_fixups", "num_sparse_rows", "small_blocks", "sparse_mean_degree")
 
 
 def save_preprocessed(path: str, blk_offsets: torch.Tensor, hspa_packed: torch.Tensor, hind: torch.Tensor,
