@@ -127,9 +127,9 @@ typedef struct {
   float sparse_mean_degree;    /* non-zeros per row over sparse_rows; <= 0 = unknown (warp-per-row kernel) */
 } vx_plan_t;
 
-/* `stages` (models 0 and 3) = K-steps of 16 gathered rows kept in flight; it selects a compiled variant, each with its
- * own number of producer warps: 8 (4 warps), 16 (4), 24 (8), 32 (8, the default for any other value), 36 (12), 40 (24),
- * 42 (14).  36 and 42 are the fast ones on large graphs; models 3 and 4 need 24 or less. */
+/* `stages` (models 0, 3 and 4) = K-steps of 16 gathered rows one CTA keeps in flight; it selects a compiled variant, each with
+ * its own number of producer warps and of CTAs sharing an SM: 14 (7 warps, 3 CTAs per SM; the default for any other value),
+ * 22 (11, 2), 15 (5, 3), 42 (14, 1), 16 (4, 2), 12 (6, 3), 24 (8, 1).  Models 3 and 4 take 12 or 24. */
 int vx_spmm(const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind, int32_t num_nodes,
             int32_t num_edges, int32_t embedding_dim, const void *input, int32_t input_dtype, float *output,
             int32_t model, int32_t stages, const vx_plan_t *plan, void *stream);

@@ -48,8 +48,8 @@ def variant(model, stages, ew):
 
 t_tiles = timeit(lambda: w._tiles.clear() or w.tiles(torch.float16))
 print(f"value tiles build: {t_tiles:.3f} ms")
-for name, fn in (("binary 42/14", variant(0, 42, None)), ("weighted tc 42/14", variant(0, 42, w)),
-                 ("weighted tc 36/12", variant(0, 36, w)), ("weighted tc 40/24", variant(0, 40, w)),
+for name, fn in (("binary 14/7", variant(0, 14, None)), ("weighted tc 14/7", variant(0, 14, w)),
+                 ("weighted tc 22/11", variant(0, 22, w)), ("weighted tc 42/14", variant(0, 42, w)),
                  ("weighted cuda-core rows (model 1)", variant(1, 32, w)),
                  ("weighted autotuned", lambda: voltrix.spmm(*st, M, nnz, feat, out=out, edge_weights=w))):
     ms = timeit(fn)

@@ -1,5 +1,5 @@
 """Parity of the SHIPPED path on the BASELINE shapes: the autotuned ``voltrix.spmm`` (whatever variant the tuner picks --
-42/14 on the large graphs) and every tensor-core variant of the tune space, against the CPU oracle on scaled instances of
+14/7 or 22/11 on the large graphs) and every tensor-core variant of the tune space, against the CPU oracle on scaled instances of
 C2 (Reddit-shaped), C4 (products-shaped) and C5 (a non-square R-MAT row shard with hub windows that get K-split).
 
 Same comparison as the reference's own test (tests/test_spmm.py:75-96: ``calc_diff`` "difference rate" against an fp32 SpMM,
@@ -15,7 +15,7 @@ import oracle
 
 pytestmark = pytest.mark.gpu
 
-HALF_VARIANTS = [(36, None), (42, None), (32, 16), (40, None)]   # the tensor-core points of SPACE_HALF
+HALF_VARIANTS = [(14, 7), (22, 11), (15, 5), (42, 14)]   # the tensor-core points of SPACE_HALF (3 / 2 / 3 / 1 CTAs per SM)
 
 
 def _scaled_err(got, want):
@@ -192,13 +192,14 @@ def test_four_feature_tiles_with_k_split_and_sparse_rows(dtype):
     st = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
     feat = torch.from_numpy(np.random.default_rng(0).standard_normal((M, N)).astype(np.float32)).cuda().to(dtype)
     want = oracle.c().spmm_csr(indptr, indices, feat.float().cpu().numpy(), 0, M, assume_coalesced=True)
-    variants = [(0, 42), (0, 40), (0, 16)] if dtype == torch.float16 else [(3, 24)]
+    variants = [(0, 14), (0, 22), (0, 15), (0, 42), (0, 40)] if dtype == torch.float16 else [(3, 24), (3, 12), (4, 12)]
     for model, stages in variants:
         o = torch.full((M, N), float("nan"), device="cuda")
         voltrix.spmm_kernel(*st, num_nodes=M, num_edges=indices.size, embedding_dim=N, input=feat, output=o, model=model,
                             stages=stages)
         assert torch.isfinite(o).all()
-        assert _scaled_err(o.cpu().numpy(), want) <= (1e-4 if dtype == torch.float16 else 2e-5), (model, stages)
+        tol = 1e-4 if dtype == torch.float16 else (5e-4 if model == 4 else 2e-5)     # model 4 carries fp32 as one fp16 term
+        assert _scaled_err(o.cpu().numpy(), want) <= tol, (model, stages)
 
 
 def _weighted_case(dtype_exact=True, seed=5):
@@ -232,7 +233,7 @@ def test_weighted_tensor_core_path_matches_scipy(dtype, N):
     w = voltrix.edge_weights(*st, torch.from_numpy(indptr), torch.from_numpy(indices), torch.from_numpy(vals))
     got = voltrix.spmm(*st, M, E, feat, edge_weights=w)
     assert torch.isfinite(got).all() and _scaled_err(got.cpu().numpy(), want) <= 1e-4
-    for model, stages, npw in [(0, 16, None), (0, 36, None), (0, 42, None), (0, 32, 16), (0, 40, None), (1, 32, None)]:
+    for model, stages, npw in [(0, 16, None), (0, 14, None), (0, 22, None), (0, 15, None), (0, 42, None), (1, 32, None)]:
         o = torch.full((M, N), float("nan"), device="cuda")
         voltrix.spmm_kernel(*st, num_nodes=M, num_edges=E, embedding_dim=N, input=feat, output=o, model=model,
                             stages=stages, npw=npw, edge_weights=w)
@@ -266,7 +267,7 @@ def test_weighted_fp32_operand_and_general_values():
     assert _scaled_err(got.cpu().numpy(), A @ f32.cpu().numpy()) <= 2e-5
     f16 = f32.half()
     o = torch.empty(M, 128, device="cuda")
-    voltrix.spmm_kernel(*st, num_nodes=M, num_edges=E, embedding_dim=128, input=f16, output=o, model=0, stages=42,
+    voltrix.spmm_kernel(*st, num_nodes=M, num_edges=E, embedding_dim=128, input=f16, output=o, model=0, stages=14,
                         edge_weights=w)
     assert _scaled_err(o.cpu().numpy(), A @ f16.float().cpu().numpy()) <= 1e-3
 
@@ -315,7 +316,7 @@ def test_fp32_single_fp16_term_path_and_its_range_fallback():
     assert _scaled_err(got.cpu().numpy(), want) <= 5e-4              # 2^-12 relative per operand value
     assert voltrix.utils.relative_error(got, torch.from_numpy(want).cuda()) <= 1e-2
     as_f16 = torch.full((M, N), float("nan"), device="cuda")
-    voltrix.spmm_kernel(*st, num_nodes=M, num_edges=E, embedding_dim=N, input=feat.half(), output=as_f16, model=0, stages=42)
+    voltrix.spmm_kernel(*st, num_nodes=M, num_edges=E, embedding_dim=N, input=feat.half(), output=as_f16, model=0, stages=14)
     tc_rows = torch.ones(M, dtype=torch.bool, device="cuda")
     tc_rows[st[1]._vx_plan.sparse_rows[: st[1]._vx_plan.num_sparse_rows].long()] = False     # sparse rows stay exact fp32
     assert torch.equal(got[tc_rows], as_f16[tc_rows])

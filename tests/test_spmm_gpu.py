@@ -16,9 +16,10 @@ DTYPES = [torch.float32, torch.float16, torch.bfloat16]
 TOL = {torch.float32: 2e-5, torch.float16: 1e-4, torch.bfloat16: 1e-4}
 
 
-# every tensor-core variant of the autotune space (jit_kernels/spmm.py::SPACE_HALF: 36/12, 42/14 -- the usual winner --,
-# 32/16, 40/24 = the two-producer-group geometry) plus the small test-only ones: (model, K-steps in flight[, producer warps])
-TC_VARIANTS = [(0, 16), (0, 32), (0, 36), (0, 42), (0, 32, 16), (0, 40)]
+# every tensor-core variant of the autotune space (jit_kernels/spmm.py::SPACE_HALF: 14/7 = three CTAs per SM, 22/11 = two,
+# 15/5 = three with 3-stage rings, 42/14 = one) plus the test-only ones (16/4, 40/24 = the two-producer-group geometry):
+# (model, K-steps in flight per CTA[, producer warps])
+TC_VARIANTS = [(0, 14), (0, 22), (0, 15), (0, 42), (0, 16), (0, 40)]
 
 
 def _scaled_err(got, want):
@@ -27,7 +28,7 @@ def _scaled_err(got, want):
 
 def _run_all_models(voltrix, blk, packed, hind, M, E, feat):
     out = {}
-    models = [(1, 32), (2, 32), (3, 24)] if feat.dtype == torch.float32 else TC_VARIANTS + [(1, 32), (2, 32)]
+    models = [(1, 32), (2, 32), (3, 24), (3, 12)] if feat.dtype == torch.float32 else TC_VARIANTS + [(1, 32), (2, 32)]
     for model, stages, *rest in models:
         o = torch.full((M, feat.shape[1]), float("nan"), device="cuda")
         try:
@@ -68,7 +69,7 @@ def test_every_path_matches_oracle(golden_cases, name, dtype, N):
     assert _scaled_err(got, want) <= TOL[dtype]
 
 
-@pytest.mark.parametrize("variant", [(16, None), (36, None), (42, None), (32, 16), (40, None)])
+@pytest.mark.parametrize("variant", [(14, None), (22, None), (15, None), (42, None), (16, None), (40, None)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_sparse_window_routing_and_k_split(dtype, variant):
     """A matrix with one hub window (split along K), many ordinary windows and very sparse windows
@@ -287,7 +288,8 @@ def test_fused_epilogue_every_model(dtype):
     blk, packed, hind = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
     plan = packed._vx_plan
     assert plan.num_fixups >= 1 and plan.num_sparse_rows > 0
-    models = [(1, 32), (2, 32), (3, 24)] if dtype == torch.float32 else [(0, 16), (0, 36), (0, 42), (0, 40), (1, 32), (2, 32)]
+    models = [(1, 32), (2, 32), (3, 24), (3, 12), (4, 12)] if dtype == torch.float32 else \
+        [(0, 14), (0, 22), (0, 15), (0, 42), (0, 40), (1, 32), (2, 32)]
     for model, stages in models:
         plain = torch.empty(M, N, device="cuda")
         voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=indices.size, embedding_dim=N, input=feat,
@@ -357,7 +359,7 @@ def test_c_abi_plan_with_epilogue():
     lib.vx_spmm.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, vp, i32, i32, ctypes.POINTER(Plan), vp]
     out = torch.full((M, N), float("nan"), device="cuda")
     rc = lib.vx_spmm(blk.data_ptr(), packed.data_ptr(), hind.data_ptr(), M, indices.size, N, feat.data_ptr(), 1,
-                     out.data_ptr(), 0, 36, ctypes.byref(plan), torch.cuda.current_stream().cuda_stream)
+                     out.data_ptr(), 0, 14, ctypes.byref(plan), torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     torch.cuda.synchronize()
     want = torch.relu(voltrix.spmm(blk, packed, hind, M, indices.size, feat) * scale[:, None] + bias[None, :])
@@ -368,7 +370,7 @@ def test_c_abi_plan_with_epilogue():
     plan.ticket = ticket.data_ptr()
     out2 = torch.full((M, N), float("nan"), device="cuda")
     rc = lib.vx_spmm(blk.data_ptr(), packed.data_ptr(), hind.data_ptr(), M, indices.size, N, feat.data_ptr(), 1,
-                     out2.data_ptr(), 0, 42, ctypes.byref(plan), torch.cuda.current_stream().cuda_stream)
+                     out2.data_ptr(), 0, 22, ctypes.byref(plan), torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     torch.cuda.synchronize()
     assert torch.equal(out2, out)

@@ -26,13 +26,13 @@ static int spmm_dispatch(const int32_t *blk_offsets, const uint32_t *hspa_packed
                   : voltrix_spmm_forward_cuda<T, KS, NPW>(blk_offsets, hspa_packed, hind, num_nodes, num_edges,         \
                                                           embedding_dim, in, output, model, plan, stream)
   switch (stages) {
-    case 8: VX_TC_VARIANT(8, 4);
+    case 12: VX_TC_VARIANT(12, 6);
+    case 15: VX_TC_VARIANT(15, 5);
     case 16: VX_TC_VARIANT(16, 4);
+    case 22: VX_TC_VARIANT(22, 11);
     case 24: VX_TC_VARIANT(24, 8);
-    case 36: VX_TC_VARIANT(36, 12);
     case 42: VX_TC_VARIANT(42, 14);
-    case 40: VX_TC_VARIANT(40, 24);
-    default: VX_TC_VARIANT(32, 8);
+    default: VX_TC_VARIANT(14, 7);
   }
 #undef VX_TC_VARIANT
 }

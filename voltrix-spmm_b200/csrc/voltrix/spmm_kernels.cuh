@@ -172,7 +172,7 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
       if (rc != VX_OK) return rc;
       Epilogue carried = plan.epilogue;      // the fp16 carrier is 2^s times the operand: scale the accumulator back
       carried.pow2_max_bits = flag + 1;
-      rc = launch_spmm_tc<__half, 42, 14, 1>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
+      rc = launch_spmm_tc<__half, 14, 7, 1>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
                                              hspa_packed, hind, num_nodes, b_rows, embedding_dim, as_half, output,
                                              plan.scratch, stream, carried, plan.ticket, flag, 0);
       if (rc != VX_OK) return rc;

@@ -50,6 +50,11 @@
 #ifndef VX_TC_EXP
 #define VX_TC_EXP 0
 #endif
+// Probe: force the number of resident CTAs per SM the persistent kernel is compiled and launched for (0 = what the
+// variant's shared memory, threads and registers allow, see tc_ctas_per_sm).
+#ifndef VX_TC_CTAS_PER_SM
+#define VX_TC_CTAS_PER_SM 0
+#endif
 
 namespace voltrix {
 
@@ -80,14 +85,23 @@ struct TcGeom {
   static constexpr int kGroups = NPW / kKsPerStage;
   static constexpr int kStageB = kKsPerStage * kKsB;
   static constexpr int kStageA = kKsPerStage * kKsA;
-  static constexpr int kStagesPerChunk = 4;             // metadata chunk = 4 stages
+  // metadata ring: 4 slots of 4-stage chunks for the one-CTA-per-SM variants; the small rings that share an SM keep
+  // 3 slots of 2-stage chunks (every byte of shared memory they do not spend is ring depth for the co-resident CTA)
+  static constexpr int kStagesPerChunk = NPW <= 11 ? 2 : 4;
   static constexpr int kChunkBlks = 2 * kKsPerStage * kStagesPerChunk;   // TC blocks per metadata chunk
-  static constexpr int kMetaSlots = 4;
+  static constexpr int kMetaSlots = NPW <= 11 ? 3 : 4;
   static constexpr int kMetaH = kChunkBlks * 32;        // hind bytes per chunk
   static constexpr int kMetaP = kChunkBlks * 16;        // bitmap bytes per chunk
-  static constexpr int kEpilogueWarp0 = (NPW + 3) / 4 * 4;   // epilogue warp e reads TMEM lanes 32*(warp % 4)...
-  static constexpr int kMmaWarp = kEpilogueWarp0 + 4, kLoaderWarp = kEpilogueWarp0 + 5;
-  static constexpr int kThreads = (kEpilogueWarp0 + 6) * 32;
+  // Warp layout: producers 0..NPW-1; the four epilogue warps start at a multiple of 4 (epilogue warp e may only read TMEM
+  // lanes 32 * (warp % 4) ...); the MMA and loader warps go wherever that costs fewer warps -- right behind the producers
+  // (filling the gap up to the next multiple of 4) or behind the epilogue warps.  Fewer threads = more co-resident CTAs.
+  static constexpr int kWarpsTail = (NPW + 3) / 4 * 4 + 6;        // [producers][pad][epilogue x4][mma][loader]
+  static constexpr int kWarpsGap = (NPW + 2 + 3) / 4 * 4 + 4;     // [producers][mma][loader][pad][epilogue x4]
+  static constexpr bool kServiceInGap = kWarpsGap < kWarpsTail;
+  static constexpr int kEpilogueWarp0 = kServiceInGap ? (NPW + 2 + 3) / 4 * 4 : (NPW + 3) / 4 * 4;
+  static constexpr int kMmaWarp = kServiceInGap ? NPW : kEpilogueWarp0 + 4;
+  static constexpr int kLoaderWarp = kMmaWarp + 1;
+  static constexpr int kThreads = (kServiceInGap ? kWarpsGap : kWarpsTail) * 32;
   static constexpr uint32_t kTmemCols = 32;             // two 16-column accumulators
   static constexpr int kUnitSlots = 4;                  // work-unit ring (loader -> every other role), 32 B per slot
   static constexpr int kUnitConsumers = NPW + 5;        // producer warps + MMA warp + 4 epilogue warps
@@ -107,8 +121,23 @@ constexpr size_t tc_smem_bytes() {
 // element (row r, column slot c) of type T at (r >> 3) * 128 + (r & 7) * 16 + c * 2 -- exactly the K-major shared-memory image
 // of one 8-column chunk of the A^T operand (core matrices 128 B apart along the window rows, 256 B apart along K), so a
 // K-step's A^T tile is ONE 512-byte bulk copy from global memory into the stage and the producers expand nothing.
+// Resident CTAs per SM.  Two or three small rings on one SM mean two or three MMA-issuing warps: the ~68 clk a 128x16x16
+// tcgen05.mma costs back to back is a per-issuer cost, and with co-resident CTAs the tensor core, the TMA unit
+// and the shared-memory port are kept busy by one CTA while another waits on a barrier (Reddit-shaped C2, N=128 fp16: 42/14 with
+// one CTA per SM 1.88 ms, 20/10 with two 1.71 ms).  Bounded by shared memory (228 KB per SM, 1 KB reserved per CTA), threads
+// (2048) and registers (the kernel needs 48; __launch_bounds__ holds the compiler to what the count allows).
+template <int KSTEPS, int NPW, int TERMS = 1>
+constexpr int tc_ctas_per_sm() {
+  if (VX_TC_CTAS_PER_SM > 0) return VX_TC_CTAS_PER_SM;
+  constexpr int by_smem = int((228 * 1024) / (tc_smem_bytes<KSTEPS, NPW, TERMS>() + 1024));
+  constexpr int by_threads = 2048 / TcGeom<NPW, TERMS>::kThreads;
+  constexpr int by_regs = 65536 / (TcGeom<NPW, TERMS>::kThreads * 40);   // the kernel compiles to 40-48 registers
+  constexpr int m = by_smem < by_threads ? (by_smem < by_regs ? by_smem : by_regs) : (by_threads < by_regs ? by_threads : by_regs);
+  return m < 1 ? 1 : (m > 4 ? 4 : m);
+}
+
 template <typename T, int KSTEPS, int NPW, int TERMS = 1, bool WEIGHTED = false>
-__global__ void __launch_bounds__(TcGeom<NPW, TERMS>::kThreads, 1)
+__global__ void __launch_bounds__(TcGeom<NPW, TERMS>::kThreads, tc_ctas_per_sm<KSTEPS, NPW, TERMS>())
 vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__restrict__ items, int32_t num_items,
                   int32_t n_feat_tiles, const int32_t *__restrict__ blk_offsets, const uint4 *__restrict__ packed,
                   const int4 *__restrict__ hind4, int32_t num_nodes, int32_t N, float *__restrict__ C,
@@ -585,7 +614,8 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
   VX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int32_t n_feat_tiles = ceil_div(N, G::kFeatTile);
   const int64_t total_units = int64_t(num_items) * n_feat_tiles;
-  const int grid = int(total_units < device_sm_count() ? total_units : device_sm_count());
+  const int64_t resident = int64_t(device_sm_count()) * tc_ctas_per_sm<STAGES, NPW, TERMS>();
+  const int grid = int(total_units < resident ? total_units : resident);
   // `ticket` (4 bytes of device memory owned by the caller, one per stream in flight): dynamic unit claiming.
   // Zeroed here, on the stream, so a launch never depends on how the previous one ended; nullptr = static striding.
   if (ticket != nullptr) VX_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int32_t), stream));

@@ -34,6 +34,8 @@ def all_variants():
         out.append(("spmm_kernel", {"ctype": ctype, "weighted": "false"}, space, spmm.includes, spmm.arg_defs_for(dtype),
                     spmm.template))
         wspace = spmm.SPACE_FP32_WEIGHTED if dtype == torch.float32 else spmm.SPACE_HALF_WEIGHTED + ({"model": 0, "stages": 16, "npw": 4},)
+        if dtype == torch.float32:
+            space = space + ({"model": 3, "stages": 24, "npw": 8},) if {"model": 3, "stages": 24, "npw": 8} not in space else space
         out.append(("spmm_kernel", {"ctype": ctype, "weighted": "true"}, wspace, spmm.includes, spmm.arg_defs_for(dtype),
                     spmm.template))
         if dtype != torch.float32:

@@ -47,16 +47,19 @@ __return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}, {npw}, {we
 
 _CTYPE = {torch.float32: "float", torch.float16: "__half", torch.bfloat16: "__nv_bfloat16"}
 
-# autotune space per input dtype: (model, stages)
-SPACE_HALF = ({"model": 0, "stages": 36, "npw": 12}, {"model": 0, "stages": 42, "npw": 14}, {"model": 0, "stages": 32, "npw": 16},
-              {"model": 0, "stages": 40, "npw": 24}, {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
-# variants reachable only through the explicit model=/stages= arguments (tests, scripts): prebuilt as well
-EXTRA_HALF = ({"model": 0, "stages": 16, "npw": 4}, {"model": 0, "stages": 32, "npw": 8})
+# autotune space per input dtype: (model, K-steps in flight per CTA, producer warps per CTA).  The tensor-core variants differ
+# in how many CTAs share an SM (csrc/voltrix/spmm_tcgen05.cuh::tc_ctas_per_sm): 14/7 three, 22/11 and 15/5 ... two / three, 42/14
+# one.  Several small rings per SM = several MMA-issuing warps; they win on every shape measured (profiles/r2n_multi_cta_variants.txt).
+SPACE_HALF = ({"model": 0, "stages": 14, "npw": 7}, {"model": 0, "stages": 22, "npw": 11}, {"model": 0, "stages": 15, "npw": 5},
+              {"model": 0, "stages": 42, "npw": 14}, {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
+# variants reachable only through the explicit model=/stages=/npw= arguments (tests, scripts): prebuilt as well
+EXTRA_HALF = ({"model": 0, "stages": 16, "npw": 4}, {"model": 0, "stages": 40, "npw": 24})
 # fp32: model 4 = tcgen05 on ONE fp16 term when the operand is inside fp16's normal range (else model 3's pipeline, decided on
 # the device); model 3 = tcgen05 on two bf16 terms (hi + lo); models 1 / 2 = exact-fp32 CUDA-core rows
-SPACE_FP32 = ({"model": 4, "stages": 24, "npw": 8}, {"model": 3, "stages": 24, "npw": 8}, {"model": 1, "stages": 32, "npw": 8},
-              {"model": 2, "stages": 32, "npw": 8})
-
+SPACE_FP32 = ({"model": 4, "stages": 12, "npw": 6}, {"model": 3, "stages": 12, "npw": 6}, {"model": 3, "stages": 24, "npw": 8},
+              {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
+# producer warps of a variant named by its K-step count alone (explicit model=/stages= calls without npw=)
+DEFAULT_NPW = {8: 4, 10: 5, 12: 6, 14: 7, 15: 5, 16: 4, 20: 10, 21: 7, 22: 11, 24: 8, 32: 8, 36: 12, 40: 24, 42: 14}
 
 # A with per-edge values: the WEIGHTED tensor-core instantiations and the weighted CUDA-core CSR rows
 SPACE_HALF_WEIGHTED = tuple(c for c in SPACE_HALF if c["model"] in (0, 1))
@@ -227,8 +230,8 @@ def spmm_kernel(
             value_tiles = edge_weights.tiles(input.dtype)
             assert value_tiles.numel() == plan.total_blocks * 128
     if model is not None:   # explicit variant (tests, benchmarks): a space of one, no timing runs
-        stages = int(stages or (24 if int(model) in (3, 4) else 32))
-        npw = int(npw or {8: 4, 16: 4, 36: 12, 42: 14, 40: 24}.get(stages, 8))
+        stages = int(stages or (12 if int(model) in (3, 4) else 14))
+        npw = int(npw or DEFAULT_NPW.get(stages, 8))
         space = ({"model": int(model), "stages": stages, "npw": npw},)
         keys = {"ctype": _CTYPE[input.dtype], "fixed": f"{model}/{stages}/{npw}"}
     elif weighted:
