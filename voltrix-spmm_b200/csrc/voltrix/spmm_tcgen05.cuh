@@ -15,25 +15,28 @@
 //   * D^T lives in TMEM (128 lanes x 16 fp32 columns, double buffered across work items) and is read
 //     back with tcgen05.ld 32x32b: a thread holds the 16 window rows of one feature, so every store
 //     instruction of a warp writes 32 consecutive floats of one C row;
-//   * a K-step is 16 gathered rows (two TC blocks); a pipeline stage is NPW K-steps (one per producer warp: 12 x (4 KB of
-//     B rows + 512 B of A^T) in the 36/12 variant), so the MMA warp pays one mbarrier wait and one tcgen05.commit per stage;
-//   * warp roles (NPW + 6 warps): 0..NPW-1 producers -- warp w owns K-step w of every stage: it expands the two bitmaps
-//     into the A^T tile with all 32 lanes (nibble table in shared memory, one STS.128 per lane), then ONE elected lane
-//     issues the 8 gather4 copies (elect.sync keeps the TMA operands in uniform registers: no per-lane serialisation
-//     loop); next 4 warps = epilogue (TMEM lane quarter = warp % 4); then the MMA issuer + TMEM owner; then the metadata
-//     loader, which streams each item's hind / bitmap arrays into a shared-memory ring with 1-D bulk copies so the
-//     producers never wait on a global load;
-//   * full/empty mbarriers per stage (tcgen05.commit frees a stage when the MMAs that read it retire),
-//     full/empty per metadata chunk, full/empty per TMEM accumulator;
+//   * a K-step is 16 gathered rows (two TC blocks); a pipeline stage is NPW K-steps (one per producer warp: 7 x (4 KB of
+//     B rows + 512 B of A^T) in the 14/7 variant), so the MMA warp pays one mbarrier wait and one tcgen05.commit per stage;
+//   * warp roles: NPW producers -- warp w owns K-step w of every stage: it expands the two bitmaps into the A^T tile with all
+//     32 lanes (nibble table in shared memory, one STS.128 per lane), then ONE elected lane issues the 8 gather4 copies
+//     (elect.sync keeps the TMA operands in uniform registers: no per-lane serialisation loop); 4 epilogue warps (TMEM lane
+//     quarter = warp % 4); the MMA issuer + TMEM owner; the loader, which is the CTA's scheduler and streams each item's
+//     hind / bitmap arrays into a shared-memory ring with 1-D bulk copies so the producers never wait on a global load;
+//   * full/empty mbarriers per stage (tcgen05.commit frees a stage when the MMAs that read it retire), full/empty per
+//     metadata chunk, per TMEM accumulator and per slot of the unit ring;
 //   * persistent CTAs claim units (feature tile, item) from the LPT-sorted work list (schedule.cuh) with an atomic
-//     ticket, feature-tile-major; the loader lane is the CTA's scheduler and publishes each unit to the other
-//     roles through a small shared-memory ring (static striding when the caller passes no ticket counter);
-//   * TERMS = 2 (fp32 input as two bf16 terms) doubles the gathered tile and the MMAs of a K-step, same accumulator;
+//     ticket, feature-tile-major; the loader lane publishes each unit to the other roles through a small shared-memory ring
+//     (static striding when the caller passes no ticket counter);
+//   * TWO OR THREE CTAs PER SM (tc_ctas_per_sm): small rings, several MMA-issuing warps per SM -- the ~68 clk a back-to-back
+//     tcgen05.mma costs is a per-issuer cost, and co-resident CTAs fill one another's barrier waits;
+//   * TERMS = 2 (fp32 input as two bf16 terms) doubles the gathered tile and the MMAs of a K-step, same accumulator; fp32
+//     input as ONE fp16 term runs the TERMS = 1 kernel behind a device-side range gate (spmm_kernels.cuh, model 4);
+//   * WEIGHTED: per-edge values arrive as ready-made A^T tiles by bulk copy, nothing is expanded;
 //   * the optional Epilogue (row scale / bias / ReLU) is applied to whole-window items here and to K-split windows in
 //     vx_spmm_fixup_kernel.
-// What paces it (measured, profiles/r1c_bottleneck_isolation.md): a 128x16x16 MMA costs ~68 clk back to back, TMA writes 32
-// and the tensor core reads 36 shared-memory wavefronts per K-step, and the L2 slices deliver the gather at 86 % of their
-// peak at best -- three floors of 61-68 clk per K-step; the kernel runs at ~79.
+// What paces it (profiles/r1c_bottleneck_isolation.md, profiles/r2n_multi_cta_variants.txt): TMA writes 32 and the tensor core
+// reads 36 shared-memory wavefronts per K-step (68 clk at one per clock) and the L2 slices deliver the gather at 86 % of their
+// peak at best (61 clk); the 14/7 variant runs at ~70 clk per K-step on the L2-resident Reddit-shaped graph.
 #ifndef VOLTRIX_B200_SPMM_TCGEN05_CUH_
 #define VOLTRIX_B200_SPMM_TCGEN05_CUH_
 
