@@ -373,15 +373,20 @@ def parity_check(indptr_h, indices_h, row0, feat, out_rows, budget_nnz: int, nco
 
 def host_link_floor(world: int, h2d_bytes: int, d2h_bytes: int):
     """What the host<->device links of this pool's boxes allow for the end-to-end leg (measured, profiles/host_links.json):
-    the larger of the two directions at the aggregate bandwidth k concurrently copying GPUs reach with both directions busy."""
+    the slower direction of a step at the aggregate bandwidth `world` concurrently copying GPUs reach -- with that direction
+    alone on the links (a floor) and with both directions busy (what a fully overlapped pipeline sees most of the time)."""
     try:
         with open(os.path.join(ROOT, "profiles", "host_links.json")) as f:
             db = json.load(f)
-        bw = db["both"].get(str(world))
-        if bw is None:
+        k = str(world)
+        if k not in db["d2h"]:
             return None
-        ms = max(h2d_bytes, d2h_bytes) / (bw * 2**30) * 1e3
-        return {"ms_per_step": ms, "aggregate_gib_s_per_direction": bw, "source": db["source"]}
+        gib = float(2**30)
+        alone = max(d2h_bytes / (db["d2h"][k] * gib), h2d_bytes / (db["h2d"][k] * gib)) * 1e3      # each direction by itself
+        duplex = max(d2h_bytes, h2d_bytes) / (db["both"][k] * gib) * 1e3                            # both directions busy
+        return {"ms_per_step": alone, "ms_per_step_both_directions_busy": duplex,
+                "aggregate_gib_s": {"d2h": db["d2h"][k], "h2d": db["h2d"][k], "both_per_direction": db["both"][k]},
+                "source": db["source"]}
     except Exception:
         return None
 
