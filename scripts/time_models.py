@@ -46,10 +46,12 @@ variants = [(0, 16, 4), (0, 32, 8), (0, 36, 12), (1, 32, 8), (2, 32, 8)] if dt !
 if args.only:
     variants = [tuple(int(x) for x in v.split("/")) for v in args.only.split(",")]
 ref = None
-for model, stages, npw in variants:
+for model, stages, npw, *rest in variants:
+    ft = rest[0] if rest else None
+
     def run():
         voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=nnz, embedding_dim=N, input=feat, output=out,
-                            model=model, stages=stages, npw=npw)
+                            model=model, stages=stages, npw=npw, ft=ft)
     if args.once:
         run(); torch.cuda.synchronize(); flush.zero_(); run(); torch.cuda.synchronize()
         print(f"ran model {model} stages {stages} npw {npw} once (after one warm-up)")
@@ -69,5 +71,5 @@ for model, stages, npw in variants:
         ts.append(s.elapsed_time(e))
     ms = float(np.median(ts))
     gather = plan.total_blocks * 8 * N * feat.element_size() if model != 1 else nnz * N * feat.element_size()
-    print(f"model {model} stages {stages:2d} npw {npw:2d}: {ms:8.3f} ms  {2.0 * nnz * N / ms / 1e6:9.1f} GFLOP/s  "
+    print(f"model {model} stages {stages:2d} npw {npw:2d} ft {ft or 128:3d}: {ms:8.3f} ms  {2.0 * nnz * N / ms / 1e6:9.1f} GFLOP/s  "
           f"gather {gather / ms / 1e6:8.1f} GB/s  (min {min(ts):.3f} max {max(ts):.3f})")

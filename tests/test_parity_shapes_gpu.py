@@ -215,7 +215,7 @@ def _weighted_case(dtype_exact=True, seed=5):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("N", [64, 128, 256])
+@pytest.mark.parametrize("N", [32, 64, 128, 256])
 def test_weighted_tensor_core_path_matches_scipy(dtype, N):
     """A with per-edge values on the tcgen05 kernel (value tiles bulk-copied straight into the A^T operand stage) -- every
     tensor-core variant, the weighted CUDA-core model and the autotuned entry point against scipy on the same operand;
@@ -233,10 +233,14 @@ def test_weighted_tensor_core_path_matches_scipy(dtype, N):
     w = voltrix.edge_weights(*st, torch.from_numpy(indptr), torch.from_numpy(indices), torch.from_numpy(vals))
     got = voltrix.spmm(*st, M, E, feat, edge_weights=w)
     assert torch.isfinite(got).all() and _scaled_err(got.cpu().numpy(), want) <= 1e-4
-    for model, stages, npw in [(0, 16, None), (0, 14, None), (0, 22, None), (0, 15, None), (0, 42, None), (1, 32, None)]:
+    variants = [(0, 16, None, None), (0, 14, None, None), (0, 22, None, None), (0, 15, None, None), (0, 42, None, None),
+                (1, 32, None, None)]
+    if N <= 64:      # the 64-wide feature tile takes the value tiles as well
+        variants += [(0, 20, 10, 64), (0, 21, 7, 64), (0, 33, 11, 64)]
+    for model, stages, npw, ft in variants:
         o = torch.full((M, N), float("nan"), device="cuda")
         voltrix.spmm_kernel(*st, num_nodes=M, num_edges=E, embedding_dim=N, input=feat, output=o, model=model,
-                            stages=stages, npw=npw, edge_weights=w)
+                            stages=stages, npw=npw, edge_weights=w, ft=ft)
         assert torch.isfinite(o).all(), (model, stages)
         assert _scaled_err(o.cpu().numpy(), want) <= 1e-4, (model, stages, npw)
     # fused epilogue on top of the weighted product

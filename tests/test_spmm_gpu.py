@@ -20,6 +20,8 @@ TOL = {torch.float32: 2e-5, torch.float16: 1e-4, torch.bfloat16: 1e-4}
 # 15/5 = three with 3-stage rings, 42/14 = one) plus the test-only ones (16/4, 40/24 = the two-producer-group geometry):
 # (model, K-steps in flight per CTA[, producer warps])
 TC_VARIANTS = [(0, 14), (0, 22), (0, 15), (0, 42), (0, 16), (0, 40)]
+# the 64-wide feature tile (MMA M = 64) of SPACE_HALF_NARROW, for dense operands of at most 64 columns: (model, stages, npw, ft)
+TC_VARIANTS_NARROW = [(0, 20, 10, 64), (0, 21, 7, 64), (0, 33, 11, 64)]
 
 
 def _scaled_err(got, want):
@@ -29,11 +31,14 @@ def _scaled_err(got, want):
 def _run_all_models(voltrix, blk, packed, hind, M, E, feat):
     out = {}
     models = [(1, 32), (2, 32), (3, 24), (3, 12)] if feat.dtype == torch.float32 else TC_VARIANTS + [(1, 32), (2, 32)]
+    if feat.dtype != torch.float32 and feat.shape[1] <= 64:
+        models = models + TC_VARIANTS_NARROW
     for model, stages, *rest in models:
         o = torch.full((M, feat.shape[1]), float("nan"), device="cuda")
         try:
             voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=E, embedding_dim=feat.shape[1], input=feat,
-                                output=o, model=model, stages=stages, npw=rest[0] if rest else None)
+                                output=o, model=model, stages=stages, npw=rest[0] if rest else None,
+                                ft=rest[1] if len(rest) > 1 else None)
         except RuntimeError as e:
             if "invalid argument" in str(e):   # model 1 without CSR (duplicates in the input)
                 continue
@@ -69,14 +74,16 @@ def test_every_path_matches_oracle(golden_cases, name, dtype, N):
     assert _scaled_err(got, want) <= TOL[dtype]
 
 
-@pytest.mark.parametrize("variant", [(14, None), (22, None), (15, None), (42, None), (16, None), (40, None)])
+@pytest.mark.parametrize("variant", [(14, None), (22, None), (15, None), (42, None), (16, None), (40, None),
+                                     (20, 10, 64), (21, 7, 64), (33, 11, 64)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_sparse_window_routing_and_k_split(dtype, variant):
     """A matrix with one hub window (split along K), many ordinary windows and very sparse windows
     (routed to the CUDA-core row path): all three mechanisms in one SpMM, result equals the oracle."""
     import voltrix
     rng = np.random.default_rng(3)
-    M, N = 4096, 128
+    ft = variant[2] if len(variant) > 2 else None
+    M, N = 4096, (128 if ft is None else 48)      # the 64-wide tile with a width that is not a multiple of 64 either
     rows, cols = [], []
     for r in range(M):
         if r < 16:
@@ -98,10 +105,10 @@ def test_sparse_window_routing_and_k_split(dtype, variant):
     feat = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32)).cuda().to(dtype)
     p1, pk, hi = oracle.c().csr_to_tiles(indptr, indices)
     want = oracle.c().spmm_tiles(p1, pk, hi, M, feat.float().cpu().numpy())
-    stages, npw = variant
+    stages, npw = variant[0], variant[1]
     o = torch.full((M, N), float("nan"), device="cuda")
     voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=indices.size, embedding_dim=N, input=feat, output=o,
-                        model=0, stages=stages, npw=npw)
+                        model=0, stages=stages, npw=npw, ft=ft)
     got = o.cpu().numpy()
     assert np.isfinite(got).all()
     assert _scaled_err(got, want) <= 1e-4
@@ -109,7 +116,7 @@ def test_sparse_window_routing_and_k_split(dtype, variant):
     for _ in range(3):
         o2 = torch.empty_like(o)
         voltrix.spmm_kernel(blk, packed, hind, num_nodes=M, num_edges=indices.size, embedding_dim=N, input=feat, output=o2,
-                            model=0, stages=stages, npw=npw)
+                            model=0, stages=stages, npw=npw, ft=ft)
         assert torch.equal(o, o2)
 
 

@@ -55,7 +55,7 @@ template <> struct TcSupported<__nv_bfloat16> { static constexpr bool value = tr
 // A with per-edge values (no reference counterpart): model 0 runs the WEIGHTED instantiation of
 // the tensor-core kernel on plan.value_tiles (+ weighted CUDA-core rows for the sparse windows), model 1 the weighted
 // CUDA-core rows on plan.csr_values.  16-bit dense operands ride the tensor cores; fp32 operands use model 1.
-template <typename T, int STAGES, int NPW>
+template <typename T, int STAGES, int NPW, int FT = 128>
 inline int voltrix_spmm_weighted_forward_cuda(const int32_t *blks_offsets, const int32_t *hind, int num_nodes,
                                               int num_edges, int embedding_dim, const T *input, float *output, int model,
                                               const SpmmPlan &plan, cudaStream_t stream) {
@@ -64,7 +64,7 @@ inline int voltrix_spmm_weighted_forward_cuda(const int32_t *blks_offsets, const
     if constexpr (TcSupported<T>::value) {
       if (plan.items == nullptr || plan.value_tiles == nullptr) return VX_ERR_INVALID_ARG;
       if (plan.num_fixups > 0 && plan.scratch == nullptr) return VX_ERR_INVALID_ARG;
-      int rc = launch_spmm_tc<T, STAGES, NPW, 1, true>(plan.items, plan.num_items, plan.fixups, plan.num_fixups,
+      int rc = launch_spmm_tc<T, STAGES, NPW, 1, true, FT>(plan.items, plan.num_items, plan.fixups, plan.num_fixups,
                                                        blks_offsets, static_cast<const uint32_t *>(plan.value_tiles), hind,
                                                        num_nodes, b_rows, embedding_dim, input, output, plan.scratch,
                                                        stream, plan.epilogue, plan.ticket);
@@ -88,14 +88,15 @@ inline int voltrix_spmm_weighted_forward_cuda(const int32_t *blks_offsets, const
   return VX_ERR_UNSUPPORTED;
 }
 
-template <typename T, int STAGES = 32, int NPW = 8, bool WEIGHTED = false>
+// FT (feature tile = MMA M, 128 or 64) applies to model 0; the 64-wide tile is for embedding_dim <= 64.
+template <typename T, int STAGES = 32, int NPW = 8, bool WEIGHTED = false, int FT = 128>
 inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t *hspa_packed, const int32_t *hind,
                                      int num_nodes, int num_edges, int embedding_dim, const T *input, float *output,
                                      int model, const SpmmPlan &plan, cudaStream_t stream) {
   if (num_nodes < 0 || embedding_dim <= 0) return VX_ERR_INVALID_ARG;
   if (num_nodes == 0) return VX_OK;
   if constexpr (WEIGHTED)
-    return voltrix_spmm_weighted_forward_cuda<T, STAGES, NPW>(blks_offsets, hind, num_nodes, num_edges, embedding_dim,
+    return voltrix_spmm_weighted_forward_cuda<T, STAGES, NPW, FT>(blks_offsets, hind, num_nodes, num_edges, embedding_dim,
                                                               input, output, model, plan, stream);
   const int32_t W = ceil_div<int32_t>(num_nodes, BLK_H);
   const int64_t b_rows = plan.input_rows > 0 ? plan.input_rows : num_nodes;
@@ -104,7 +105,7 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
       int rc;
       if (plan.items != nullptr) {
         if (plan.num_fixups > 0 && plan.scratch == nullptr) return VX_ERR_INVALID_ARG;
-        rc = launch_spmm_tc<T, STAGES, NPW>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
+        rc = launch_spmm_tc<T, STAGES, NPW, 1, false, FT>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
                                        hspa_packed, hind, num_nodes, b_rows, embedding_dim, input,
                                        output, plan.scratch, stream, plan.epilogue, plan.ticket);
         if (rc != VX_OK) return rc;
@@ -114,7 +115,7 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
                                   embedding_dim, input, output, stream, plan.sparse_mean_degree, plan.epilogue);
         }
       } else {
-        rc = launch_spmm_tc<T, STAGES, NPW>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind, num_nodes, b_rows,
+        rc = launch_spmm_tc<T, STAGES, NPW, 1, false, FT>(nullptr, W, nullptr, 0, blks_offsets, hspa_packed, hind, num_nodes, b_rows,
                                        embedding_dim, input, output, nullptr, stream, plan.epilogue, plan.ticket);
       }
       return rc;

@@ -75,11 +75,16 @@ template <> struct TcFmt<__nv_bfloat16> {
 // tensor map) whose products accumulate into the same TMEM tile.  TERMS = 1 for fp16 / bf16 input; TERMS = 2 is the fp32
 // path: x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (16 mantissa bits, full fp32 exponent range; the reference
 // rounds fp32 to TF32 = 10 mantissa bits, spmm_kernels.cuh:1631-1678).
-template <int NPW, int TERMS = 1>
+// FT: features per work unit = MMA M.  128 fills the tensor core's M; 64 is for dense operands of at most 64 columns: the M = 64
+// instruction reads one 128-byte swizzle atom per gathered row instead of two, which is what such a launch is bound by
+// (the second atom would be padding: Reddit-shaped N = 64 ran as fast as N = 128 with the 128-wide tile).
+template <int NPW, int TERMS = 1, int FT = 128>
 struct TcGeom {
-  static constexpr int kFeatTile = 128;                 // MMA M: features per work unit
+  static_assert(FT == 128 || FT == 64, "feature tile = MMA M: 128 or 64");
+  static constexpr int kFeatTile = FT;                  // MMA M: features per work unit
   static constexpr int kAtomCols = 64;                  // 128-byte swizzle span in 16-bit elements
-  static constexpr int kTermB = kFeatTile * 16 * 2;     // one term of one K-step: 16 gathered rows x 128 features x 2 B = 4096
+  static constexpr int kTermB = kFeatTile * 16 * 2;     // one term of one K-step: 16 gathered rows x FT features x 2 B (4096 / 2048)
+  static constexpr int kKGroupB = kFeatTile * 8 * 2;    // 8 gathered rows (one k-group): FT / 64 swizzle atoms of 1024 B
   static constexpr int kKsB = kTermB * TERMS;           // one K-step, all terms
   static constexpr int kKsA = 16 * 16 * 2;              // one K-step: densified 16 x 16 tile = 512
   // K-steps per stage.  Up to 16 producer warps: one stage = one K-step per warp.  More warps: stages of 8
@@ -111,9 +116,9 @@ struct TcGeom {
 };
 
 // KSTEPS = K-steps in flight (the autotuned "stages" knob): ring depth = KSTEPS / NPW stages.
-template <int KSTEPS, int NPW, int TERMS = 1>
+template <int KSTEPS, int NPW, int TERMS = 1, int FT = 128>
 constexpr size_t tc_smem_bytes() {
-  using G = TcGeom<NPW, TERMS>;
+  using G = TcGeom<NPW, TERMS, FT>;
   constexpr int S = KSTEPS / G::kKsPerStage;
   return size_t(S) * (G::kStageB + G::kStageA) + size_t(G::kMetaSlots) * (G::kMetaH + G::kMetaP) +
          (2 * S + 2 * G::kMetaSlots + 4 + 2 * G::kUnitSlots) * 8 + 16 + 128 /*nibble table*/ + G::kUnitSlots * 32 +
@@ -129,24 +134,24 @@ constexpr size_t tc_smem_bytes() {
 // and the shared-memory port are kept busy by one CTA while another waits on a barrier (Reddit-shaped C2, N=128 fp16: 42/14 with
 // one CTA per SM 1.88 ms, 20/10 with two 1.71 ms).  Bounded by shared memory (228 KB per SM, 1 KB reserved per CTA), threads
 // (2048) and registers (the kernel needs 48; __launch_bounds__ holds the compiler to what the count allows).
-template <int KSTEPS, int NPW, int TERMS = 1>
+template <int KSTEPS, int NPW, int TERMS = 1, int FT = 128>
 constexpr int tc_ctas_per_sm() {
   if (VX_TC_CTAS_PER_SM > 0) return VX_TC_CTAS_PER_SM;
-  constexpr int by_smem = int((228 * 1024) / (tc_smem_bytes<KSTEPS, NPW, TERMS>() + 1024));
-  constexpr int by_threads = 2048 / TcGeom<NPW, TERMS>::kThreads;
-  constexpr int by_regs = 65536 / (TcGeom<NPW, TERMS>::kThreads * 40);   // the kernel compiles to 40-48 registers
+  constexpr int by_smem = int((228 * 1024) / (tc_smem_bytes<KSTEPS, NPW, TERMS, FT>() + 1024));
+  constexpr int by_threads = 2048 / TcGeom<NPW, TERMS, FT>::kThreads;
+  constexpr int by_regs = 65536 / (TcGeom<NPW, TERMS, FT>::kThreads * 40);   // the kernel compiles to 40-48 registers
   constexpr int m = by_smem < by_threads ? (by_smem < by_regs ? by_smem : by_regs) : (by_threads < by_regs ? by_threads : by_regs);
   return m < 1 ? 1 : (m > 4 ? 4 : m);
 }
 
-template <typename T, int KSTEPS, int NPW, int TERMS = 1, bool WEIGHTED = false>
-__global__ void __launch_bounds__(TcGeom<NPW, TERMS>::kThreads, tc_ctas_per_sm<KSTEPS, NPW, TERMS>())
+template <typename T, int KSTEPS, int NPW, int TERMS = 1, bool WEIGHTED = false, int FT = 128>
+__global__ void __launch_bounds__(TcGeom<NPW, TERMS, FT>::kThreads, tc_ctas_per_sm<KSTEPS, NPW, TERMS, FT>())
 vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__restrict__ items, int32_t num_items,
                   int32_t n_feat_tiles, const int32_t *__restrict__ blk_offsets, const uint4 *__restrict__ packed,
                   const int4 *__restrict__ hind4, int32_t num_nodes, int32_t N, float *__restrict__ C,
                   float *__restrict__ scratch, int32_t term_stride, Epilogue epi, int32_t *__restrict__ ticket,
                   const int32_t *__restrict__ gate, int32_t gate_want) {
-  using G = TcGeom<NPW, TERMS>;
+  using G = TcGeom<NPW, TERMS, FT>;
   // Optional launch gate (fp32 operands, model 4): two alternative pipelines are enqueued and a flag written by an earlier
   // kernel on the stream decides which one runs; the other returns here, before it touches a barrier or TMEM.
   if (gate != nullptr && *gate != gate_want) return;
@@ -305,11 +310,12 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
       ptx::tma_gather4(d, &tmap, bar, c, r.x, r.y, r.z, r.w);
 #endif
     };
+    constexpr uint32_t KG = G::kKGroupB;    // byte distance of the second 8-row k-group of a K-step
     WorkItem it;
     int32_t c_base;
     while (next_unit(uc, it, c_base)) {
       const int32_t c1 = c_base + G::kAtomCols;
-      const bool two_halves = c1 < N;
+      const bool two_halves = FT == 128 && c1 < N;     // the 64-wide tile has one swizzle atom per gathered row
       const int32_t nks = (it.blk_count + 1) >> 1;
       const int32_t nst = (nks + G::kKsPerStage - 1) / G::kKsPerStage;
       const int32_t full_ks = it.blk_count >> 1;    // K-steps with both TC blocks present
@@ -371,17 +377,17 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
                 g4(d + 1024, bar, cb, r0);
                 g4(d + 512, bar, ca, r1);
                 g4(d + 1536, bar, cb, r1);
-                g4(d + 2048, bar, ca, r2);
-                g4(d + 3072, bar, cb, r2);
-                g4(d + 2560, bar, ca, r3);
-                g4(d + 3584, bar, cb, r3);
+                g4(d + KG, bar, ca, r2);
+                g4(d + KG + 1024, bar, cb, r2);
+                g4(d + KG + 512, bar, ca, r3);
+                g4(d + KG + 1536, bar, cb, r3);
               }
             } else {
               const int4 r0 = ptx::lds128(ha), r1 = ptx::lds128(ha + 16);
               int4 r2 = make_int4(0, 0, 0, 0), r3 = make_int4(0, 0, 0, 0);   // tail: row 0, bitmap bits are 0
               if (has_b1) { r2 = ptx::lds128(ha + 32); r3 = ptx::lds128(ha + 48); }
               const uint32_t vbytes = WEIGHTED ? (has_b1 ? 512u : 256u) : 0u;
-              ptx::mbar_arrive_expect_tx(bar, uint32_t(two_halves ? G::kKsB : G::kKsB / 2) + vbytes);
+              ptx::mbar_arrive_expect_tx(bar, uint32_t(two_halves || FT == 64 ? G::kKsB : G::kKsB / 2) + vbytes);
               if constexpr (WEIGHTED)
                 ptx::bulk_g2s(sA + s * G::kStageA + uint32_t(kw) * G::kKsA, packed + (int64_t(it.blk_begin) + 2 * ks) * 16,
                               vbytes, bar);
@@ -391,13 +397,13 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
                 const int32_t ca = c_base + t * term_stride, cb = c1 + t * term_stride;
                 g4(d, bar, ca, r0);
                 g4(d + 512, bar, ca, r1);
-                g4(d + 2048, bar, ca, r2);
-                g4(d + 2560, bar, ca, r3);
+                g4(d + KG, bar, ca, r2);
+                g4(d + KG + 512, bar, ca, r3);
                 if (two_halves) {
                   g4(d + 1024, bar, cb, r0);
                   g4(d + 1536, bar, cb, r1);
-                  g4(d + 3072, bar, cb, r2);
-                  g4(d + 3584, bar, cb, r3);
+                  g4(d + KG + 1024, bar, cb, r2);
+                  g4(d + KG + 1536, bar, cb, r3);
                 }
               }
             }
@@ -418,7 +424,7 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
     }
   } else if (warp == G::kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = ptx::make_idesc(TcFmt<T>::kFmt, /*A MN-major*/ true, /*B K-major*/ false, 128, 16);
+    constexpr uint32_t idesc = ptx::make_idesc(TcFmt<T>::kFmt, /*A MN-major*/ true, /*B K-major*/ false, FT, 16);
     uint32_t s = 0, par = 0, unit = 0, uc = 0;
     WorkItem it;
     int32_t c_base;
@@ -439,7 +445,7 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
           // B = densified tile: K-major, no swizzle, LBO = k-chunk stride (128), SBO = 8-row group stride (256)
           // Only the 14-bit start-address field changes from K-step to K-step (+4096 B / +512 B, no carry out of
           // the field: shared memory is < 256 KB), so the low words are advanced by constants.
-          const uint64_t a_desc = ptx::smem_desc(sB + s * G::kStageB, 1024, 2048, ptx::kLayoutSw128);
+          const uint64_t a_desc = ptx::smem_desc(sB + s * G::kStageB, 1024, G::kKGroupB, ptx::kLayoutSw128);
           // (value tiles: one TC block = 256 contiguous bytes, so k-chunk stride 256 and 8-row group stride 128)
           const uint64_t b_desc = WEIGHTED ? ptx::smem_desc(sA + s * G::kStageA, 256, 128, ptx::kLayoutNone)
                                            : ptx::smem_desc(sA + s * G::kStageA, 128, 256, ptx::kLayoutNone);
@@ -478,7 +484,10 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
     WorkItem it;
     int32_t c_base;
     while (next_unit(uc, it, c_base)) {
-      const int32_t f = c_base + ew * 32 + lane;
+      // M = 128: TMEM lane = feature, a warp reads its 32-lane quarter.  M = 64: the accumulator's 64 rows sit in lanes
+      // 0-15 of every quarter (rows 16 e ... 16 e + 15 in quarter e; scripts/probes/tmem_m64_probe.cu), the other lanes idle.
+      const bool holds_row = FT == 128 || lane < 16;
+      const int32_t f = FT == 128 ? c_base + ew * 32 + lane : c_base + ew * 16 + lane;
       uint32_t v[16];
       if (it.blk_count > 0) {
         const uint32_t acc = unit & 1u;
@@ -494,7 +503,7 @@ vx_spmm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const WorkItem *__re
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = 0u;
       }
-      if (f < N) {
+      if (holds_row && f < N) {
         float *dst;
         int32_t nrows = BLK_H;
         if (it.slot < 0) {
@@ -594,7 +603,7 @@ inline int device_sm_count() {
 // Launch the tensor-core kernel over a prepared work list.  B must be 16-byte aligned with N % 8 == 0
 // (TMA global-stride rule); hind / hspa_packed must be 16-byte aligned.
 // `B` holds TERMS column blocks of N elements per row (row stride TERMS * N): plain fp16 / bf16 input has TERMS = 1.
-template <typename T, int STAGES, int NPW, int TERMS = 1, bool WEIGHTED = false>
+template <typename T, int STAGES, int NPW, int TERMS = 1, bool WEIGHTED = false, int FT = 128>
 inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupItem *fixups, int32_t num_fixups,
                           const int32_t *blk_offsets, const uint32_t *hspa_packed, const int32_t *hind,
                           int32_t num_nodes, int64_t b_rows,
@@ -608,16 +617,16 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
   CUtensorMap tmap;
   int rc = make_gather_tensor_map(&tmap, B, TcFmt<T>::kTmapType, 2, b_rows, int64_t(N) * TERMS);
   if (rc != VX_OK) return rc;
-  using G = TcGeom<NPW, TERMS>;
-  auto kern = vx_spmm_tc_kernel<T, STAGES, NPW, TERMS, WEIGHTED>;
-  constexpr size_t smem = tc_smem_bytes<STAGES, NPW, TERMS>();
+  using G = TcGeom<NPW, TERMS, FT>;
+  auto kern = vx_spmm_tc_kernel<T, STAGES, NPW, TERMS, WEIGHTED, FT>;
+  constexpr size_t smem = tc_smem_bytes<STAGES, NPW, TERMS, FT>();
   static_assert(smem <= 227 * 1024, "stage ring does not fit in shared memory");
   // Set on every launch (~1 us): a function-local `static bool` would be a GNU_UNIQUE symbol shared by every
   // JIT artefact / library that instantiates this template, while each of them owns a distinct kernel copy.
   VX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const int32_t n_feat_tiles = ceil_div(N, G::kFeatTile);
   const int64_t total_units = int64_t(num_items) * n_feat_tiles;
-  const int64_t resident = int64_t(device_sm_count()) * tc_ctas_per_sm<STAGES, NPW, TERMS>();
+  const int64_t resident = int64_t(device_sm_count()) * tc_ctas_per_sm<STAGES, NPW, TERMS, FT>();
   const int grid = int(total_units < resident ? total_units : resident);
   // `ticket` (4 bytes of device memory owned by the caller, one per stream in flight): dynamic unit claiming.
   // Zeroed here, on the stream, so a launch never depends on how the previous one ended; nullptr = static striding.

@@ -30,13 +30,15 @@ def all_variants():
         ("schedule_kernel", {}, tuple(), tiles._sched_includes, tiles._sched_arg_defs, tiles._sched_template),
     ]
     for dtype, ctype in spmm._CTYPE.items():
-        space = spmm.SPACE_FP32 if dtype == torch.float32 else spmm.SPACE_HALF + spmm.EXTRA_HALF
-        out.append(("spmm_kernel", {"ctype": ctype, "weighted": "false"}, space, spmm.includes, spmm.arg_defs_for(dtype),
+        space = spmm.SPACE_FP32 if dtype == torch.float32 else \
+            spmm.SPACE_HALF + spmm.EXTRA_HALF + tuple(c for c in spmm.SPACE_HALF_NARROW if c.get("ft") == 64)
+        out.append(("spmm_kernel", {"ctype": ctype, "weighted": "false", "ft": 128}, space, spmm.includes, spmm.arg_defs_for(dtype),
                     spmm.template))
-        wspace = spmm.SPACE_FP32_WEIGHTED if dtype == torch.float32 else spmm.SPACE_HALF_WEIGHTED + ({"model": 0, "stages": 16, "npw": 4},)
+        wspace = spmm.SPACE_FP32_WEIGHTED if dtype == torch.float32 else spmm.SPACE_HALF_WEIGHTED + \
+            ({"model": 0, "stages": 16, "npw": 4},) + tuple(c for c in spmm.SPACE_HALF_NARROW if c.get("ft") == 64)
         if dtype == torch.float32:
             space = space + ({"model": 3, "stages": 24, "npw": 8},) if {"model": 3, "stages": 24, "npw": 8} not in space else space
-        out.append(("spmm_kernel", {"ctype": ctype, "weighted": "true"}, wspace, spmm.includes, spmm.arg_defs_for(dtype),
+        out.append(("spmm_kernel", {"ctype": ctype, "weighted": "true", "ft": 128}, wspace, spmm.includes, spmm.arg_defs_for(dtype),
                     spmm.template))
         if dtype != torch.float32:
             out.append(("value_tiles_kernel", {"ctype": ctype}, tuple(), value_tiles.includes, value_tiles.arg_defs_for(dtype),

@@ -40,7 +40,7 @@ plan.epilogue.relu = relu;
 plan.ticket = ticket;
 plan.value_tiles = value_tiles;
 plan.csr_values = csr_values;
-__return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}, {npw}, {weighted}>(
+__return_code = voltrix::voltrix_spmm_forward_cuda<{ctype}, {stages}, {npw}, {weighted}, {ft}>(
     blk_offsets, hspa_packed, hind,
     num_nodes, num_edges, embedding_dim, input, output, {model}, plan, stream);
 """
@@ -52,6 +52,11 @@ _CTYPE = {torch.float32: "float", torch.float16: "__half", torch.bfloat16: "__nv
 # one.  Several small rings per SM = several MMA-issuing warps; they win on every shape measured (profiles/r2n_multi_cta_variants.txt).
 SPACE_HALF = ({"model": 0, "stages": 14, "npw": 7}, {"model": 0, "stages": 22, "npw": 11}, {"model": 0, "stages": 15, "npw": 5},
               {"model": 0, "stages": 42, "npw": 14}, {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
+# dense operands of at most 64 columns: the 64-wide feature tile (MMA M = 64, one swizzle atom per gathered row), deeper rings
+# for the same bytes in flight; the 128-wide 14/7 stays in as the control
+SPACE_HALF_NARROW = ({"model": 0, "stages": 20, "npw": 10, "ft": 64}, {"model": 0, "stages": 21, "npw": 7, "ft": 64},
+                     {"model": 0, "stages": 33, "npw": 11, "ft": 64}, {"model": 0, "stages": 14, "npw": 7},
+                     {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
 # variants reachable only through the explicit model=/stages=/npw= arguments (tests, scripts): prebuilt as well
 EXTRA_HALF = ({"model": 0, "stages": 16, "npw": 4}, {"model": 0, "stages": 40, "npw": 24})
 # fp32: model 4 = tcgen05 on ONE fp16 term when the operand is inside fp16's normal range (else model 3's pipeline, decided on
@@ -59,7 +64,7 @@ EXTRA_HALF = ({"model": 0, "stages": 16, "npw": 4}, {"model": 0, "stages": 40, "
 SPACE_FP32 = ({"model": 4, "stages": 12, "npw": 6}, {"model": 3, "stages": 12, "npw": 6}, {"model": 3, "stages": 24, "npw": 8},
               {"model": 1, "stages": 32, "npw": 8}, {"model": 2, "stages": 32, "npw": 8})
 # producer warps of a variant named by its K-step count alone (explicit model=/stages= calls without npw=)
-DEFAULT_NPW = {8: 4, 10: 5, 12: 6, 14: 7, 15: 5, 16: 4, 20: 10, 21: 7, 22: 11, 24: 8, 32: 8, 36: 12, 40: 24, 42: 14}
+DEFAULT_NPW = {8: 4, 10: 5, 12: 6, 14: 7, 15: 5, 16: 4, 20: 10, 21: 7, 22: 11, 24: 8, 32: 8, 33: 11, 36: 12, 40: 24, 42: 14}
 
 # A with per-edge values: the WEIGHTED tensor-core instantiations and the weighted CUDA-core CSR rows
 SPACE_HALF_WEIGHTED = tuple(c for c in SPACE_HALF if c["model"] in (0, 1))
@@ -188,8 +193,9 @@ def spmm_kernel(
     bias=None,
     relu=False,
     edge_weights=None,
+    ft=None,
 ):
-    """Extensions beyond the reference's signature: ``plan`` / ``model`` / ``stages`` / ``npw`` (explicit variant), the
+    """Extensions beyond the reference's signature: ``plan`` / ``model`` / ``stages`` / ``npw`` / ``ft`` (explicit variant), the
     fused epilogue ``output = act(row_scale[:, None] * (A @ input) + bias[None, :])`` with fp32 ``row_scale [num_nodes]``,
     fp32 ``bias [embedding_dim]`` and ``act`` = ReLU when ``relu`` (all optional, applied in the kernel that writes C), and
     ``edge_weights`` (``voltrix.edge_weights(...)``): A carries a value per stored entry instead of 1."""
@@ -197,7 +203,7 @@ def spmm_kernel(
     # with the operand pointers patched in (see _FastLaunch).
     stream = current_stream()
     sid = int(stream.cuda_stream)
-    fast_key = (embedding_dim, input.dtype, sid, model, stages, npw, id(edge_weights) if edge_weights is not None else 0,
+    fast_key = (embedding_dim, input.dtype, sid, model, stages, npw, ft, id(edge_weights) if edge_weights is not None else 0,
                 id(plan) if plan is not None else 0, fp32_mode() if input.dtype == torch.float32 else "")
     fast = getattr(hspa_packed, "_vx_fast", None)
     if fast is not None:
@@ -232,19 +238,21 @@ def spmm_kernel(
     if model is not None:   # explicit variant (tests, benchmarks): a space of one, no timing runs
         stages = int(stages or (12 if int(model) in (3, 4) else 14))
         npw = int(npw or DEFAULT_NPW.get(stages, 8))
-        space = ({"model": int(model), "stages": stages, "npw": npw},)
-        keys = {"ctype": _CTYPE[input.dtype], "fixed": f"{model}/{stages}/{npw}"}
+        space = ({"model": int(model), "stages": stages, "npw": npw, "ft": int(ft or 128)},)
+        keys = {"ctype": _CTYPE[input.dtype], "fixed": f"{model}/{stages}/{npw}/{int(ft or 128)}"}
     elif weighted:
-        space = SPACE_FP32_WEIGHTED if input.dtype == torch.float32 else SPACE_HALF_WEIGHTED
+        space = SPACE_FP32_WEIGHTED if input.dtype == torch.float32 else \
+            tuple(c for c in (SPACE_HALF_NARROW if embedding_dim <= 64 else SPACE_HALF) if c["model"] in (0, 1))
         keys = {"ctype": _CTYPE[input.dtype], "feature_hash": feature_hash(hspa_packed), "N": embedding_dim, "plan": "pcw"}
     else:
-        space = fp32_space() if input.dtype == torch.float32 else SPACE_HALF
+        space = fp32_space() if input.dtype == torch.float32 else (SPACE_HALF_NARROW if embedding_dim <= 64 else SPACE_HALF)
         # the key also says what the plan can do: a winner found with the CSR arrays (model 1) or a work list must not
         # be replayed on a matrix that came without them under the same user-chosen hash_tag
         caps = ("p" if plan is not None else "-") + ("c" if plan is not None and plan.csr_indptr is not None else "-")
         keys = {"ctype": _CTYPE[input.dtype], "feature_hash": feature_hash(hspa_packed), "N": embedding_dim, "plan": caps}
 
     keys["weighted"] = "true" if weighted else "false"
+    keys["ft"] = 128          # default feature tile; a candidate that names its own overrides it
     if input.dtype == torch.float32 and model is None:
         keys["fp32"] = fp32_mode()      # winners are per precision class
 
