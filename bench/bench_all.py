@@ -3,8 +3,8 @@ graph_gen.py, run each method as a subprocess, parse its `[X] ... time: ` line, 
 (`Method,Dataset,FeatDim,Reorder,Time (ms)`).  Differences: graphs are the synthetic suite of
 voltrix.graphs.named_suite(); the N sweep is 32/64/128/256/512 (BASELINE.json configs[2]); methods are the ones
 that exist on this box -- cuSPARSE and Voltrix (fp32 / fp16), plus the competitors bench/competitors/build.py compiled
-for sm_100a from the reference's own sources into bench/_competitors/ (GE-SpMM, TC-GNN, RoDe, Sputnik; fp32, like the
-reference's columns).  DTC-SpMM is not built (torch extension on top of cmake builds of glog and Sputnik)."""
+for sm_100a from the reference's own sources into bench/_competitors/ (GE-SpMM, TC-GNN, RoDe, Sputnik, DTC-SpMM; fp32, like
+the reference's columns)."""
 import argparse
 import csv
 import os
@@ -24,6 +24,8 @@ if os.path.exists(os.path.join(COMP, "gespmm")):
     METHODS["GE-SPMM"] = ([os.path.join(COMP, "gespmm")], "[GE-SPMM] Embedding time: ")
 if os.path.exists(os.path.join(COMP, "tcgnn")):
     METHODS["TC-GNN"] = ([os.path.join(COMP, "tcgnn")], "[TC-GNN] Kernel time: ")
+if os.path.exists(os.path.join(COMP, "dtc", "DTCSpMM.so")):
+    METHODS["DTC-SPMM"] = ([sys.executable, os.path.join(HERE, "bm_dtc.py")], "[DTC-SPMM] Elapsed time: ")
 if os.path.isdir(os.path.join(COMP, "rode", "build", "eval")):
     METHODS["RoDe"] = ([sys.executable, os.path.join(HERE, "bm_rode.py")], "[RoDe] Elapsed time: ")
     METHODS["Sputnik"] = ([sys.executable, os.path.join(HERE, "bm_sputnik.py")], "[Sputnik] Elapsed time: ")
@@ -65,9 +67,11 @@ def main():
                             print(f"graph_gen failed for {ds}: {r.stderr[-300:]}")
                             continue
                         for method, (cmd, marker) in METHODS.items():
-                            competitor = method in ("GE-SPMM", "TC-GNN", "RoDe", "Sputnik")
-                            if competitor and (args.no_competitors or reorder):     # the reference runs them un-reordered
+                            competitor = method in ("GE-SPMM", "TC-GNN", "RoDe", "Sputnik", "DTC-SPMM")
+                            if competitor and args.no_competitors:
                                 continue
+                            if competitor and reorder != (method == "DTC-SPMM" and args.reorder):
+                                continue     # the reference runs DTC-SpMM on the reordered graph, the others un-reordered
                             if method in ("RoDe", "Sputnik"):
                                 if fd not in RODE_DIMS or not os.path.exists(os.path.join(tmp, "data.mtx")):
                                     continue

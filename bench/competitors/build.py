@@ -14,9 +14,12 @@ GPU box like every other built artefact):
                         with two small stand-in headers (bench/competitors/shims) for the CHECK macros and the uniform
                         random draw RoDe's matrix utilities take from glog / abseil.
 
-Not built: DTC-SpMM (a torch extension linked against cmake builds of glog and Sputnik, third-party/build_dtc.sh).
+  dtc/DTCSpMM.so       third-party/DTC-SpMM/DTC-SpMM: the DTC-SpMM torch extension (reference build: third-party/build_dtc.sh,
+                        `setup.py install` against cmake builds of glog and Sputnik).  Here torch.utils.cpp_extension
+                        compiles the two sources in place; the Sputnik headers it includes for one baseline entry point the
+                        harness never calls are replaced by a stub (bench/competitors/shims/sputnik).
 
-    python bench/competitors/build.py [--ref /root/reference] [--force]
+    python bench/competitors/build.py [--ref /root/reference] [--force] [--dtc]
 """
 import argparse
 import os
@@ -80,12 +83,31 @@ def build_rode(ref: str, force: bool):
     return targets
 
 
-def build(ref: str = "/root/reference", force: bool = False):
+def build_dtc(ref: str, force: bool) -> str:
+    dst = os.path.join(OUT, "dtc", "DTCSpMM.so")
+    src = os.path.join(ref, "third-party", "DTC-SpMM", "DTC-SpMM")
+    if not force and os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(os.path.join(src, "DTCSpMM_kernel.cu")):
+        return dst
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    os.environ["TORCH_CUDA_ARCH_LIST"] = "10.0a"
+    from torch.utils.cpp_extension import load
+    with tempfile.TemporaryDirectory() as tmp:
+        load(name="DTCSpMM", sources=[os.path.join(src, "DTCSpMM.cpp"), os.path.join(src, "DTCSpMM_kernel.cu")],
+             extra_include_paths=[os.path.join(HERE, "shims"), src], extra_cuda_cflags=["-O3", "-w", "--expt-relaxed-constexpr"],
+             extra_cflags=["-O2", "-w"], build_directory=tmp, verbose=False, is_python_module=False)
+        shutil.copy(os.path.join(tmp, "DTCSpMM.so"), dst)
+    return dst
+
+
+def build(ref: str = "/root/reference", force: bool = False, dtc: bool = False):
+    """``dtc``: also (re)build the DTC-SpMM torch extension -- about four minutes of nvcc, so only on request."""
     if not os.path.isdir(os.path.join(ref, "bench", "scripts")):
         raise FileNotFoundError(f"reference tree not found at {ref}")
     os.makedirs(OUT, exist_ok=True)
     built = [build_standalone(ref, n, force) for n in ("gespmm", "tcgnn")]
     built += build_rode(ref, force)
+    if dtc:
+        built.append(build_dtc(ref, force))
     return built
 
 
@@ -93,6 +115,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default=os.environ.get("VOLTRIX_REF", "/root/reference"))
     ap.add_argument("--force", action="store_true")
+    ap.add_argument("--dtc", action="store_true", help="also build the DTC-SpMM torch extension (~4 min)")
     a = ap.parse_args()
-    for path in build(a.ref, a.force):
+    for path in build(a.ref, a.force, a.dtc):
         print(os.path.relpath(path, os.path.join(HERE, "..", "..")))

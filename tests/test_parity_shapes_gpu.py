@@ -338,3 +338,33 @@ def test_fp32_single_fp16_term_path_and_its_range_fallback():
     assert torch.equal(got2, run(3, feat2))
     # and back: the flag is re-evaluated on every call
     assert torch.equal(run(4, feat), got)
+
+
+@pytest.mark.parametrize("N", [32, 64, 48])
+def test_fp32_single_fp16_term_narrow_widths(N):
+    """Model 4 at N <= 64 runs its fp16 term on the 64-wide feature tile (tcgen05.mma M = 64); same bar as N = 128, the
+    range fallback still lands on model 3's result, and a width that is not a multiple of 16 takes the masked epilogue."""
+    import voltrix
+    from test_spmm_gpu import _epilogue_case
+    indptr, indices, M = _epilogue_case()
+    E = indices.size
+    st = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
+    B = np.random.default_rng(40 + N).standard_normal((M, N)).astype(np.float32)
+    B[np.abs(B) < 1e-3] = 0.25
+    feat = torch.from_numpy(B).cuda()
+    want = oracle.c().spmm_csr(indptr, indices, B, 0, M, assume_coalesced=True, acc64=True)
+
+    def run(model, x):
+        o = torch.full((M, N), float("nan"), device="cuda")
+        voltrix.spmm_kernel(*st, num_nodes=M, num_edges=E, embedding_dim=N, input=x, output=o, model=model)
+        return o
+
+    got = run(4, feat)
+    assert torch.isfinite(got).all()
+    assert _scaled_err(got.cpu().numpy(), want) <= 5e-4
+    feat2 = feat.clone(); feat2[5, 1] = 3.0e9
+    want2 = oracle.c().spmm_csr(indptr, indices, feat2.cpu().numpy(), 0, M, assume_coalesced=True, acc64=True)
+    got2 = run(4, feat2)
+    assert _scaled_err(got2.cpu().numpy(), want2) <= 2e-5
+    assert torch.equal(got2, run(3, feat2))
+    assert torch.equal(run(4, feat), got)

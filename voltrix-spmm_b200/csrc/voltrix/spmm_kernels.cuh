@@ -173,9 +173,14 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
       if (rc != VX_OK) return rc;
       Epilogue carried = plan.epilogue;      // the fp16 carrier is 2^s times the operand: scale the accumulator back
       carried.pow2_max_bits = flag + 1;
-      rc = launch_spmm_tc<__half, 14, 7, 1>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
-                                             hspa_packed, hind, num_nodes, b_rows, embedding_dim, as_half, output,
-                                             plan.scratch, stream, carried, plan.ticket, flag, 0);
+      if (embedding_dim <= 64)   // the 64-wide feature tile, as for 16-bit operands of that width
+        rc = launch_spmm_tc<__half, 20, 10, 1, false, 64>(plan.items, plan.num_items, plan.fixups, plan.num_fixups,
+                                                          blks_offsets, hspa_packed, hind, num_nodes, b_rows, embedding_dim,
+                                                          as_half, output, plan.scratch, stream, carried, plan.ticket, flag, 0);
+      else
+        rc = launch_spmm_tc<__half, 14, 7, 1>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
+                                              hspa_packed, hind, num_nodes, b_rows, embedding_dim, as_half, output,
+                                              plan.scratch, stream, carried, plan.ticket, flag, 0);
       if (rc != VX_OK) return rc;
       rc = launch_split_bf16x2(input, terms, b_rows, embedding_dim, stream, flag, 1);
       if (rc != VX_OK) return rc;
