@@ -90,6 +90,11 @@ def build_dtc(ref: str, force: bool) -> str:
         return dst
     os.makedirs(os.path.dirname(dst), exist_ok=True)
     os.environ["TORCH_CUDA_ARCH_LIST"] = "10.0a"
+    # link with the distribution's g++: a toolchain wrapper whose libstdc++.so is missing falls back to libstdc++.a, and a
+    # second copy of the locale facets inside the extension crashes the first `std::cout << number` in a torch process
+    for var, tool in (("CC", "/usr/bin/gcc"), ("CXX", "/usr/bin/g++")):
+        if os.path.exists(tool):
+            os.environ[var] = tool
     from torch.utils.cpp_extension import load
     with tempfile.TemporaryDirectory() as tmp:
         load(name="DTCSpMM", sources=[os.path.join(src, "DTCSpMM.cpp"), os.path.join(src, "DTCSpMM_kernel.cu")],

@@ -45,3 +45,35 @@ def test_rode_output_line_parsing(tmp_path, monkeypatch):
     assert got == {"Sputnik": 1.25, "cuSPARSE (RoDe driver)": 2.0, "RoDe": 0.75}
     with pytest.raises(FileNotFoundError):
         bm_rode.run_eval(str(home), 512, "data.mtx")
+
+
+def test_plot_report_from_results_csv(tmp_path):
+    """bench/plot.py (reference bench/plot.py:1-146 without matplotlib/seaborn): speed-ups over cuSPARSE per cell, a method
+    with no row is 'n/a', cells without a cuSPARSE row are dropped, and the SVG parses."""
+    import importlib.util
+    import xml.dom.minidom
+    spec = importlib.util.spec_from_file_location("vx_plot", os.path.join(ROOT, "bench", "plot.py"))
+    plot = importlib.util.module_from_spec(spec); spec.loader.exec_module(plot)
+    res = tmp_path / "results.csv"
+    res.write_text("Method,Dataset,FeatDim,Reorder,Time (ms)\n"
+                   "cuSPARSE,ddi,128,False,0.4\nVoltrix,ddi,128,False,0.1\nRoDe,ddi,128,False,0.2\n"
+                   "cuSPARSE,ddi,256,False,0.8\nVoltrix,ddi,256,False,0.4\nRoDe,ddi,256,False,NAN\n"
+                   "Voltrix,ppi,128,False,0.3\n"
+                   "cuSPARSE,ddi,128,True,0.4\nVoltrix,ddi,128,True,0.05\n")
+    sp = plot.speedups(plot.read_results(str(res)))
+    assert set(sp) == {"ddi", "ddi.reorder", "ppi"} and sp["ppi"] == {}
+    assert sp["ddi"][128] == {"cuSPARSE": 1.0, "Voltrix": 4.0, "RoDe": 2.0}
+    assert "RoDe" not in sp["ddi"][256] and sp["ddi.reorder"][128]["Voltrix"] == 8.0
+    md = plot.markdown(sp)
+    assert "| ddi | 256 | 1.00x | n/a | 2.00x |" in md and "geomean" in md
+    xml.dom.minidom.parseString(plot.svg(sp))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "bench", "_competitors", "dtc", "DTCSpMM.so")),
+                    reason="DTC-SpMM extension not built (python bench/competitors/build.py --dtc)")
+def test_dtc_extension_shares_the_process_libstdcxx():
+    """A DTCSpMM.so that carries its own libstdc++.a (what a toolchain wrapper with a dangling libstdc++.so produces) holds
+    a second set of locale facet ids and segfaults on its first `std::cout << number` inside a torch process."""
+    so = os.path.join(ROOT, "bench", "_competitors", "dtc", "DTCSpMM.so")
+    needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
+    assert "libstdc++.so.6" in needed
