@@ -198,16 +198,23 @@ def test_properties_at_scale(dtype):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("N", [32, 64, 128, 512])
-def test_low_degree_rows_use_group_per_row_kernel(dtype, N):
-    """Mean degree ~3 (the Yeast / DD end of the C3 suite): the CSR path switches to one lane group per row
-    (vx_csr_subwarp_rows_kernel); result equals the oracle's CSR SpMM, rows without non-zeros are written as 0."""
+@pytest.mark.parametrize("degree", [1.7, 3.0, 5.0])
+def test_low_degree_rows_use_group_per_row_kernel(dtype, N, degree):
+    """Mean degree 2-5 (the Yeast / DD end of the C3 suite): the CSR path switches to one lane group per row
+    (vx_spmm_csr_subwarp_rows_kernel; one warp per row at N = 512).  Result equals the oracle's CSR SpMM -- bit for bit in
+    fp32, the sum being in CSR order -- including a few long rows, rows without non-zeros (written as 0) and a row count
+    that is not a multiple of the rows per warp."""
     import scipy.sparse as sp
     import voltrix
-    M = 5000
-    A = sp.random(M, M, density=3.0 / M, format="csr", random_state=np.random.default_rng(7))
-    indptr, indices = A.indptr.astype(np.int32), A.indices.astype(np.int32)
-    assert (np.diff(indptr) == 0).any()
+    M = 5003
+    A = sp.random(M, M, density=degree / M, format="lil", random_state=np.random.default_rng(7))
     rng = np.random.default_rng(N)
+    for r in (1, 2500, M - 1):                     # long rows among the short ones
+        for c in rng.choice(M, size=301, replace=False):
+            A[r, c] = 1.0
+    A = A.tocsr(); A.sort_indices()
+    indptr, indices = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    assert (np.diff(indptr) == 0).any() and indices.size / M < 6.0
     feat = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32)).cuda().to(dtype)
     blk, packed, hind = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
     want = oracle.c().spmm_csr(indptr, indices, feat.float().cpu().numpy(), 0, M, assume_coalesced=True)
@@ -217,6 +224,12 @@ def test_low_degree_rows_use_group_per_row_kernel(dtype, N):
     got = o.cpu().numpy()
     assert np.isfinite(got).all()
     assert _scaled_err(got, want) <= TOL[dtype]
+    if dtype == torch.float32:
+        short = np.diff(indptr) <= 8               # the oracle sums in the same order; long rows differ by FMA contraction at most
+        assert np.array_equal(got[short], want[short])
+    # the same rows through the public call: sparse windows go to the CSR kernel by row list, the rest to tcgen05
+    auto = voltrix.spmm(blk, packed, hind, M, indices.size, feat)
+    assert _scaled_err(auto.cpu().numpy(), want) <= max(TOL[dtype], 2e-3 if dtype == torch.float32 else 0)
 
 
 def test_fp32_tensor_core_path_precision_and_range():
