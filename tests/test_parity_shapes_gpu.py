@@ -338,6 +338,19 @@ def test_fp32_single_fp16_term_path_and_its_range_fallback():
     assert torch.equal(got2, run(3, feat2))
     # and back: the flag is re-evaluated on every call
     assert torch.equal(run(4, feat), got)
+    # stray values close to zero (any large Gaussian operand has some) do not re-route the call: the gate counts groups
+    # with a value below fp16's normal range, it does not look at the minimum
+    feat3 = feat.clone(); feat3[11, 5] = 1.0e-12; feat3[900, 77] = -3.0e-20
+    got3 = run(4, feat3)
+    want3 = oracle.c().spmm_csr(indptr, indices, feat3.cpu().numpy(), 0, M, assume_coalesced=True, acc64=True)
+    assert _scaled_err(got3.cpu().numpy(), want3) <= 5e-4
+    as_f16_3 = torch.full((M, N), float("nan"), device="cuda")
+    voltrix.spmm_kernel(*st, num_nodes=M, num_edges=E, embedding_dim=N, input=feat3.half(), output=as_f16_3, model=0, stages=14)
+    assert torch.equal(got3[tc_rows], as_f16_3[tc_rows])            # still the one-term pipeline
+    assert not torch.equal(got3, run(3, feat3))
+    # rows of B far below the rest are structure, not stray values (8 groups of 128 values here; 3 are tolerated)
+    feat4 = feat.clone(); feat4[40:48] *= 1.0e-11
+    assert torch.equal(run(4, feat4), run(3, feat4))
 
 
 @pytest.mark.parametrize("N", [32, 64, 48])

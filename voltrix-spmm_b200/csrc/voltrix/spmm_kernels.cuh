@@ -159,14 +159,15 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
     }
   } else if (model == 4) {
     // fp32 input at the reference's precision class, at fp16 cost: the operand is rounded to fp16 (11 significant bits; the
-    // reference rounds to TF32's 10) and runs the one-term tensor-core kernel -- unless a value falls outside fp16's normal
-    // range, which the conversion pass detects; then the gated two-term bf16 pipeline of model 3 runs instead.  Both
-    // pipelines are enqueued, the device flag (plan.ticket[1]) picks one: no host round trip, CUDA-graph capturable.
+    // reference rounds to TF32's 10) and runs the one-term tensor-core kernel -- unless the operand does not fit fp16's
+    // normal range after a power-of-two scaling (Inf / NaN, or more than a stray value in 10^6 below it), which the
+    // conversion pass detects; then the gated two-term bf16 pipeline of model 3 runs instead.  Both pipelines are
+    // enqueued, the device flag (plan.ticket[1]) picks one: no host round trip, CUDA-graph capturable.
     if constexpr (std::is_same<T, float>::value && tc_smem_bytes<STAGES, NPW, 2>() <= 227 * 1024) {
       if (plan.split_ws == nullptr || plan.ticket == nullptr || plan.items == nullptr) return VX_ERR_INVALID_ARG;
       if (embedding_dim % 8 != 0) return VX_ERR_UNSUPPORTED;
       if (plan.num_fixups > 0 && plan.scratch == nullptr) return VX_ERR_INVALID_ARG;
-      int32_t *flag = plan.ticket + 1;       // ticket[1..3]: flag, bits of max |x|, bits of min non-zero |x|
+      int32_t *flag = plan.ticket + 1;       // ticket[1..3]: flag, bits of max |x|, tail-group count
       __half *as_half = static_cast<__half *>(plan.split_ws);
       __nv_bfloat16 *terms = static_cast<__nv_bfloat16 *>(plan.split_ws);
       int rc = launch_cvt_f16(input, as_half, b_rows, embedding_dim, flag, stream);

@@ -683,13 +683,24 @@ inline int launch_split_bf16x2(const float *in, __nv_bfloat16 *out, int64_t rows
 // fp16 keeps 11 significant bits -- one more than the TF32 the reference rounds its operand to (spmm_kernels.cuh:1631-1678)
 // -- for values inside its normal range, 2^-14 .. 65504.  The operand is therefore scaled by a power of two (exact) that
 // puts its largest magnitude just under fp16's maximum, which leaves 2^29 of dynamic range below it; the accumulator is
-// scaled back in the epilogue.  Two passes over the operand, both on the stream, no host round trip:
-//   range pass    max |x|, min non-zero |x| (atomics on the bit patterns), non-finite values
-//   convert pass  x * 2^s -> fp16; raises `flag` if the range pass saw Inf / NaN or min |x| * 2^s < 2^-14 (an operand
-//                 spanning more than fp16's normal range) -- then the gated two-term bf16 pipeline runs instead.
-// state[0] = flag, state[1] = bits of max |x|, state[2] = bits of min non-zero |x|.
+// scaled back in the epilogue.  Three launches on the stream, no host round trip:
+//   range pass    max |x| (atomicMax on the bit pattern), non-finite values
+//   convert pass  x * 2^s -> fp16, and counts the groups of 128 consecutive values in which a non-zero value lands below
+//                 fp16's normal range (it keeps fewer than 11 bits there, none below 2^-39 of the largest magnitude)
+//   decide        flag = 1 if the operand holds Inf / NaN, if 2^s is not a normal float, or if more than one group in
+//                 kF16TailGroups (and more than kF16TailFloor groups) has such a value -- then the gated two-term bf16
+//                 pipeline runs instead.
+// The count, not the minimum, decides: one Gaussian sample in 10^8 is that close to zero, and a gate on the minimum sends a
+// large operand down the slow pipeline at random (1.8x the time); an operand with a structurally wide range -- rows or
+// columns scaled apart by more than 2^29 -- fails the count by orders of magnitude.  A value under the gate's radar carries
+// an absolute error below 2^-40 of the operand's largest magnitude.
+// state[0] = flag (after `decide`), state[1] = bits of max |x|, state[2] = tail-group count / not-representable bit.
+constexpr int32_t kF16TailGroups = 8192;          // tolerated: one 128-value group in 8192 with a sub-normal-range value
+constexpr int32_t kF16TailFloor = 3;              // small operands: a handful of stray values is still not structure
+constexpr int32_t kF16NotRepresentable = 1 << 30;
+
 __global__ void vx_spmm_absrange_kernel(const float4 *__restrict__ in, int64_t quads, int32_t *__restrict__ state) {
-  uint32_t mx = 0u, mn = 0x7f7fffffu;
+  uint32_t mx = 0u;
   bool nonfinite = false;
   for (int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < quads; q += int64_t(gridDim.x) * blockDim.x) {
     const float4 v = in[q];
@@ -699,51 +710,63 @@ __global__ void vx_spmm_absrange_kernel(const float4 *__restrict__ in, int64_t q
       const uint32_t a = __float_as_uint(x[i]) & 0x7fffffffu;
       nonfinite |= a >= 0x7f800000u;
       mx = max(mx, a);
-      if (a != 0u) mn = min(mn, a);
     }
   }
-  for (int off = 16; off > 0; off >>= 1) {
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-  }
+  for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
   nonfinite = __any_sync(0xffffffffu, nonfinite);
   if ((threadIdx.x & 31) == 0) {
     atomicMax(reinterpret_cast<unsigned int *>(state + 1), mx);
-    atomicMin(reinterpret_cast<unsigned int *>(state + 2), mn);
-    if (nonfinite) state[0] = 1;
+    if (nonfinite) atomicOr(state + 2, kF16NotRepresentable);
   }
 }
 
 __global__ void vx_spmm_cvt_f16_kernel(const float4 *__restrict__ in, __half *__restrict__ out, int64_t quads,
                                        int32_t *__restrict__ state) {
-  const int32_t max_bits = state[1], min_bits = state[2];
+  const int32_t max_bits = state[1];
   const int s = Epilogue::carrier_shift(max_bits);
-  // representable: |s| small enough for 2^s to be a normal float, and the smallest value still normal in fp16 after scaling
-  const int min_exp = ((min_bits >> 23) & 0xff) - 127;
-  const bool ok = state[0] == 0 && s > -100 && s < 100 && (max_bits == 0 || min_exp + s >= -14);
   const int64_t q = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (q == 0 && !ok) state[0] = 1;
-  if (!ok || q >= quads) return;      // the other pipeline will run: nothing to convert
-  const float k = __int_as_float((127 + s) << 23);   // 2^s
-  const float4 v = in[q];
-  __half2 h[2] = {__floats2half2_rn(v.x * k, v.y * k), __floats2half2_rn(v.z * k, v.w * k)};
-  *reinterpret_cast<uint2 *>(out + q * 4) = *reinterpret_cast<const uint2 *>(h);
+  if (!(s > -100 && s < 100)) {                 // 2^s must be a normal float
+    if (q == 0) atomicOr(state + 2, kF16NotRepresentable);
+    return;
+  }
+  bool tail = false;
+  if (q < quads) {
+    const float k = __int_as_float((127 + s) << 23);   // 2^s
+    const float4 v = in[q];
+    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t a = __float_as_uint(x[i]) & 0x7fffffffu;
+      tail |= a != 0u && int(a >> 23) - 127 + s < -14;
+    }
+    __half2 h[2] = {__floats2half2_rn(v.x * k, v.y * k), __floats2half2_rn(v.z * k, v.w * k)};
+    *reinterpret_cast<uint2 *>(out + q * 4) = *reinterpret_cast<const uint2 *>(h);
+  }
+  if (__any_sync(0xffffffffu, tail) && (threadIdx.x & 31) == 0) atomicAdd(state + 2, 1);
 }
 
-// state: 3 ints of device memory (flag, max bits, min bits), initialised here
+__global__ void vx_spmm_f16_gate_kernel(int32_t *__restrict__ state, int32_t limit) {
+  state[0] = state[2] > limit ? 1 : 0;          // the not-representable bit is far above any limit
+}
+
+// state: 3 ints of device memory (flag, max bits, tail count), initialised here
 inline int launch_cvt_f16(const float *in, __half *out, int64_t rows, int32_t N, int32_t *state, cudaStream_t stream) {
   if (N % 4 != 0 || (reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || state == nullptr)
     return VX_ERR_UNSUPPORTED;
-  VX_CUDA_TRY(cudaMemsetAsync(state, 0, 2 * sizeof(int32_t), stream));      // flag = 0, max |x| = 0
-  VX_CUDA_TRY(cudaMemsetAsync(state + 2, 0x7f, sizeof(int32_t), stream));   // min |x| = 0x7f7f7f7f (a huge finite float)
+  VX_CUDA_TRY(cudaMemsetAsync(state, 0, 3 * sizeof(int32_t), stream));      // flag = 0, max |x| = 0, tail groups = 0
   const int64_t quads = rows * (N >> 2);
   if (quads <= 0) return VX_OK;
+  const int64_t groups = (quads + 31) / 32;                                 // 128-value groups = warps of the convert pass
+  if (groups >= kF16NotRepresentable) return VX_ERR_UNSUPPORTED;            // the count shares a word with that bit
   const int64_t want_ctas = (quads + 255) / 256, cap_ctas = int64_t(device_sm_count()) * 16;
   const int grid = int(want_ctas < cap_ctas ? want_ctas : cap_ctas);
   vx_spmm_absrange_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4 *>(in), quads, state);
   VX_LAUNCH_CHECK();
   vx_spmm_cvt_f16_kernel<<<unsigned((quads + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4 *>(in), out, quads,
                                                                             state);
+  VX_LAUNCH_CHECK();
+  const int64_t tolerated = groups / kF16TailGroups;                          // ... and never fewer than kF16TailFloor groups
+  vx_spmm_f16_gate_kernel<<<1, 1, 0, stream>>>(state, int32_t(tolerated > kF16TailFloor ? tolerated : kF16TailFloor));
   VX_LAUNCH_CHECK();
   return VX_OK;
 }
