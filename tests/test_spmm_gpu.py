@@ -232,6 +232,42 @@ def test_low_degree_rows_use_group_per_row_kernel(dtype, N, degree):
     assert _scaled_err(auto.cpu().numpy(), want) <= max(TOL[dtype], 2e-3 if dtype == torch.float32 else 0)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("N", [32, 128, 512])
+def test_short_rows_at_scale_take_several_rows_per_warp(dtype, N):
+    """Above 2^17 rows of mean degree < 8 the CSR launchers give every warp (or lane group) FOUR rows: row ids and CSR
+    bounds of all four are loaded first, then the rows are walked (spmm_cuda_core.cuh, RPW).  Same result as the oracle, bit
+    for bit in fp32; row count not a multiple of 4 or 32; empty rows written as zeros; also through the row list of the
+    sparse windows (public call) and with per-entry values."""
+    import scipy.sparse as sp
+    import voltrix
+    M = (1 << 17) + 24581
+    rng = np.random.default_rng(N)
+    deg = rng.integers(0, 5, size=M); deg[rng.integers(0, M, 40)] = 70            # mostly 0-4, a few longer rows
+    pattern = sp.coo_matrix((np.ones(int(deg.sum()), np.float32), (np.repeat(np.arange(M), deg), rng.integers(0, M, int(deg.sum())))),
+                            shape=(M, M)).tocsr()
+    pattern.sum_duplicates(); pattern.sort_indices()
+    indptr, indices = pattern.indptr.astype(np.int32), pattern.indices.astype(np.int32)
+    deg = np.diff(indptr)
+    assert (deg == 0).any() and M % 4 and M % 32
+    feat = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32)).cuda().to(dtype)
+    st = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
+    want = oracle.c().spmm_csr(indptr, indices, feat.float().cpu().numpy(), 0, M, assume_coalesced=True)
+    o = torch.full((M, N), float("nan"), device="cuda")
+    voltrix.spmm_kernel(*st, num_nodes=M, num_edges=indices.size, embedding_dim=N, input=feat, output=o, model=1)
+    got = o.cpu().numpy()
+    assert np.isfinite(got).all() and _scaled_err(got, want) <= TOL[dtype]
+    if dtype == torch.float32:
+        assert np.array_equal(got[deg <= 8], want[deg <= 8])
+    assert st[1]._vx_plan.num_sparse_rows >= (1 << 17)                                # the row-list launch is RPW too
+    auto = voltrix.spmm(*st, M, indices.size, feat)
+    assert _scaled_err(auto.cpu().numpy(), want) <= max(TOL[dtype], 2e-3 if dtype == torch.float32 else 0)
+    vals = rng.uniform(0.5, 1.5, indices.size).astype(np.float32)
+    A = sp.csr_matrix((vals, indices, indptr), shape=(M, M))
+    w = voltrix.spmm_weighted(torch.from_numpy(indptr).cuda(), torch.from_numpy(indices).cuda(), torch.from_numpy(vals).cuda(), feat)
+    assert _scaled_err(w.cpu().numpy(), A @ feat.float().cpu().numpy()) <= 1e-4
+
+
 def test_fp32_tensor_core_path_precision_and_range():
     """Model 3 keeps 16 mantissa bits and the full fp32 exponent range: values far outside fp16's range and a
     mantissa pattern that TF32 (10 bits) would round away both survive."""

@@ -114,7 +114,13 @@ struct ScalarAccess {
 // row_list[0..num_rows).  grid.x * warps_per_block >= num_rows, grid.y = feature chunks.
 // WEIGHTED: `vals[e]` multiplies the gathered row of non-zero e (general CSR values).  The
 // binary instantiation is the product path of the tile format; the weighted one serves voltrix.spmm_weighted.
-template <typename T, int LANES, bool WEIGHTED = false, typename A = VecAccess<T>>
+// RPW: rows per warp.  With RPW > 1 the warp first loads the row ids and the CSR bounds of all its rows (independent loads:
+// the row_list -> indptr round trips are paid once per RPW rows) and then walks them; a launch over millions of short or
+// empty rows (the sparse windows of an R-MAT matrix: 71 % of those rows have no entry) needs RPW times fewer warps.
+// Measured with RPW = 1 / 2 / 4 / 8 (profiles/r2ac_csr_rows_per_warp.txt): the 21.8 M sparse rows of R-MAT-25 9.0 / 7.0 / 6.3 / 6.6 ms,
+// YeastH N = 512 fp16 3.00 / 2.62 / 2.36 / 2.77 ms -- 4 everywhere.  The group-per-row kernel below already packs 2-8 rows
+// into a warp; giving each group four rows made it 0-20 % slower, so it keeps one.
+template <typename T, int LANES, bool WEIGHTED = false, typename A = VecAccess<T>, int RPW = 1>
 __global__ void __launch_bounds__(256)
 vx_spmm_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                    const int32_t *__restrict__ row_list, int32_t num_rows, int32_t N,
@@ -125,12 +131,25 @@ vx_spmm_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__res
   const int lane = threadIdx.x & 31;
   const int sub = lane % LANES;               // position inside the row slice
   const int grp = lane / LANES;
-  const int32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (item >= num_rows) return;
-  const int32_t row = row_list ? row_list[item] : item;
+  const int64_t item0 = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (item0 >= num_rows) return;
   const int32_t f0 = blockIdx.y * CHUNK + sub * EPL;
   const bool active = f0 < N;
-  const int32_t beg = indptr[row], end = indptr[row + 1];
+  int32_t rows[RPW], begs[RPW], ends[RPW];
+#pragma unroll
+  for (int k = 0; k < RPW; ++k) {
+    const int64_t it = item0 + k;
+    rows[k] = it < num_rows ? (row_list ? __ldg(row_list + it) : int32_t(it)) : -1;
+  }
+#pragma unroll
+  for (int k = 0; k < RPW; ++k) {
+    begs[k] = rows[k] >= 0 ? __ldg(indptr + rows[k]) : 0;
+    ends[k] = rows[k] >= 0 ? __ldg(indptr + rows[k] + 1) : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < RPW; ++k) {
+  const int32_t row = rows[k], beg = begs[k], end = ends[k];
+  if (row < 0) break;                         // warp-uniform: every lane of the warp walks the same rows
 
   float acc[EPL];
 #pragma unroll
@@ -174,6 +193,7 @@ vx_spmm_csr_rows_kernel(const int32_t *__restrict__ indptr, const int32_t *__res
       for (int i = 0; i < EPL; ++i) acc[i] = epi.apply(acc[i], sc, epi.bias_of(f0 + i));
     }
     A::store(C + int64_t(row) * N + f0, acc);
+  }
   }
 }
 
@@ -239,7 +259,7 @@ vx_spmm_tile_rows_kernel(const int32_t *__restrict__ blk_offsets, const uint32_t
   constexpr int EPL = A::N;
   constexpr int CHUNK = 32 * EPL;
   const int lane = threadIdx.x & 31;
-  const int32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int32_t row = int32_t(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   if (row >= num_nodes) return;
   const int32_t w = row >> 4, r = row & 15;
   const int32_t f0 = blockIdx.y * CHUNK + lane * EPL;
@@ -291,6 +311,8 @@ inline bool vec_access_ok(int32_t N, int epl, const void *B, const void *C) {
   return N % epl == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
 }
 
+constexpr float kShortRowDegree = 8.f;        // rows-per-warp launch: mean degree below this ...
+constexpr int32_t kShortRowMinRows = 1 << 17;   // ... and enough rows that a quarter of the warps still fill the GPU
 // mean_degree: non-zeros per row of the rows being computed (< 0 = unknown).  Rows with fewer non-zeros than a warp
 // has lane groups go to the group-per-row kernel; the choice depends only on (mean_degree, N), never on timing.
 template <typename T>
@@ -318,6 +340,14 @@ inline int launch_csr_rows(const int32_t *indptr, const int32_t *indices, const 
     return VX_OK;
   }
   auto grid = [&](int l) { return dim3(ceil_div(num_rows, 8), ceil_div(N, l * EPL)); };
+  if (lanes == 32 && mean_degree >= 0.f && mean_degree < kShortRowDegree && num_rows >= kShortRowMinRows) {
+    // millions of short rows at full row width: several rows per warp (see the kernel's RPW note)
+    constexpr int RPW = 4;
+    vx_spmm_csr_rows_kernel<T, 32, false, VecAccess<T>, RPW><<<dim3(ceil_div(num_rows, 8 * RPW), ceil_div(N, 32 * EPL)), block, 0,
+                                                               stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
+    VX_LAUNCH_CHECK();
+    return VX_OK;
+  }
   if (lanes == 4)       vx_spmm_csr_rows_kernel<T, 4><<<grid(4), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
   else if (lanes == 8)  vx_spmm_csr_rows_kernel<T, 8><<<grid(8), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
   else if (lanes == 16) vx_spmm_csr_rows_kernel<T, 16><<<grid(16), block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi);
@@ -345,6 +375,13 @@ inline int launch_csr_rows_weighted(const int32_t *indptr, const int32_t *indice
   const int lanes = lanes_needed <= 4 ? 4 : lanes_needed <= 8 ? 8 : lanes_needed <= 16 ? 16 : 32;
   const float mean_degree = num_edges >= 0 ? float(num_edges) / float(num_rows) : 1e30f;
   dim3 block(256);
+  if (lanes == 32 && mean_degree < kShortRowDegree && num_rows >= kShortRowMinRows) {      // RPW note above
+    constexpr int RPW = 4;
+    vx_spmm_csr_rows_kernel<T, 32, true, VecAccess<T>, RPW><<<dim3(ceil_div(num_rows, 8 * RPW), ceil_div(N, 32 * EPL)), block, 0,
+                                                              stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi, vals);
+    VX_LAUNCH_CHECK();
+    return VX_OK;
+  }
   if (lanes < 32 && mean_degree < 4.f * float(32 / lanes)) {
     dim3 g(unsigned(ceil_div<int64_t>(int64_t(num_rows) * lanes, 256)), ceil_div(N, lanes * EPL));
     if (lanes == 4)      vx_spmm_csr_subwarp_rows_kernel<T, 4, true><<<g, block, 0, stream>>>(indptr, indices, row_list, num_rows, N, B, C, epi, vals);
