@@ -1,9 +1,9 @@
 #!/bin/bash
-# pass 24: count-based model-4 gate -- GPU suite, fp32 timing on the big operands (5 repeats each to see the spread), bench, C3 suite
+# final one-GPU evidence: GPU suite, smoke, C3 suite, fp32 repeatability, both bench arms
 O=gpurun_out; mkdir -p $O
-echo "== pytest -m gpu"; timeout -s KILL 900 python -m pytest tests -x -q -m gpu > $O/r2y_t_gpu.log 2>&1; echo "rc=$?"; tail -2 $O/r2y_t_gpu.log
+echo "== pytest -m gpu"; timeout -s KILL 900 python -m pytest tests -x -q -m gpu > $O/r2zz_t_gpu.log 2>&1; echo "rc=$?"; tail -2 $O/r2zz_t_gpu.log
 echo "== smoke"; timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-echo "== C3 suite"; timeout -s KILL 1500 python scripts/suite.py --out $O/r2y_suite_c3.csv > $O/r2y_suite_c3.log 2>&1; echo "rc=$?"; grep "^reddit" $O/r2y_suite_c3.log | tail -5
+echo "== C3 suite"; timeout -s KILL 1500 python scripts/suite.py --out $O/r2zz_suite_c3.csv > $O/r2zz_suite_c3.log 2>&1; echo "rc=$?"; grep "^reddit" $O/r2zz_suite_c3.log | tail -5
 echo "== reddit fp32 N=512 / N=256, repeated (fresh operand each time)"
 timeout -s KILL 600 python - <<'PY' 2>&1 | tail -12
 import sys, os, torch, numpy as np
@@ -27,5 +27,5 @@ for N in (128, 256, 512):
         res.append(round(float(np.median(ts)), 3))
     print(f"reddit fp32 N={N}: ms per operand (uniform, normal alternating) {res}", flush=True)
 PY
-echo "== bench reference arm"; timeout -s KILL 900 python bench.py --impl reference > $O/r2y_bench_ref_n1.json 2> $O/r2y_bench_ref_n1.err; echo "rc=$?"
-echo "== bench"; timeout -s KILL 1200 python bench.py > $O/r2y_bench_n1.json 2> $O/r2y_bench_n1.err; echo "rc=$?"; cut -c1-300 $O/r2y_bench_n1.json
+echo "== bench reference arm"; timeout -s KILL 900 python bench.py --impl reference > $O/r2zz_bench_ref_n1.json 2> $O/r2zz_bench_ref_n1.err; echo "rc=$?"
+echo "== bench"; timeout -s KILL 1200 python bench.py > $O/r2zz_bench_n1.json 2> $O/r2zz_bench_n1.err; echo "rc=$?"; cut -c1-300 $O/r2zz_bench_n1.json

@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 BLK_H = 16
-ROW_COST = 9    # in units of one non-zero, see ShardedSpMM.__init__
+ROW_COST = 7    # in units of one non-zero, see ShardedSpMM.__init__
 
 
 def partition_rows(weights: torch.Tensor, world_size: int, align: int = BLK_H) -> List[Tuple[int, int]]:
@@ -154,10 +154,11 @@ class ShardedSpMM:
         self.num_nodes = num_nodes
         if weights is None:
             # cost of a row ~ its non-zeros (one gathered B row each) + a fixed share of its window's work item
-            # (schedule slot, TMEM epilogue, the C row write).  Fitted on the per-rank times of the R-MAT-25 runs
-            # (N = 256; profiles/r2z_bench_n{2,8}.json): t = 0.039 ms per 10^6 non-zeros + 0.335 ms per 10^6 rows at 8
-            # GPUs => one row costs 8.6 non-zeros (7.5 with the 2-GPU ranks in the fit).  Round 1 used 12, fitted at
-            # scale 21 on the one-CTA kernel, which left the row-heavy last rank 15 % short of work at 8 GPUs.
+            # (schedule slot, TMEM epilogue, the C row write).  Fitted on the per-rank times of the 8-GPU R-MAT-25 run
+            # (N = 256; profiles/r2z_bench_n8.json and its history in DESIGN.md section 5): t = 0.039 ms per 10^6 non-zeros
+            # + 0.257 ms per 10^6 rows => one row costs 6.6 non-zeros.  Round 1 used 12 (fitted at scale 21 on the one-CTA
+            # kernel, before the CUDA-core rows took four rows per warp), which left the row-heavy last rank 15 % short of
+            # work at 8 GPUs.
             weights = (indptr[1:] - indptr[:-1]) + ROW_COST
         self.ranges = partition_rows(weights, self.world)
         self.r0, self.r1 = self.ranges[self.rank]
