@@ -381,3 +381,40 @@ def test_fp32_single_fp16_term_narrow_widths(N):
     assert _scaled_err(got2.cpu().numpy(), want2) <= 2e-5
     assert torch.equal(got2, run(3, feat2))
     assert torch.equal(run(4, feat), got)
+
+
+def test_reschedule_and_tune_routing():
+    """The routing rule (which windows leave the tensor cores for the CUDA-core rows) can be changed on a finished triple
+    (voltrix.reschedule: schedule kernels only) and picked by measurement (voltrix.tune_routing).  Every
+    rule computes the same product; prepared launches and K-split scratch of the old work list are dropped."""
+    import voltrix
+    from test_spmm_gpu import _epilogue_case
+    indptr, indices, M = _epilogue_case()
+    N, E = 128, indices.size
+    st = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M)
+    plan = st[1]._vx_plan
+    triple_before = [t.clone() for t in st]
+    feat = torch.from_numpy(np.random.default_rng(8).standard_normal((M, N)).astype(np.float32)).cuda().half()
+    want = oracle.c().spmm_csr(indptr, indices, feat.float().cpu().numpy(), 0, M, assume_coalesced=True, acc64=True)
+    base = voltrix.spmm(*st, M, E, feat)
+    assert plan.route_is_default and plan.num_sparse_rows > 0
+    default_sparse = plan.num_sparse_rows
+    voltrix.reschedule(*st, 0.0, 0)                       # everything on the tensor cores
+    assert plan.num_sparse_rows == 0 and not plan.route_is_default
+    all_tc = voltrix.spmm(*st, M, E, feat)
+    voltrix.reschedule(*st, 4.0, 64)                      # far more windows on the CUDA-core rows
+    assert plan.num_sparse_rows > default_sparse and not plan.route_is_default
+    mostly_rows = voltrix.spmm(*st, M, E, feat)
+    for got in (base, all_tc, mostly_rows):
+        assert _scaled_err(got.cpu().numpy(), want) <= 1e-4
+    best, timings = voltrix.tune_routing(*st, M, E, feat, iters=3)
+    assert best in timings and len(timings) >= 2 and timings[best] == min(timings.values())
+    assert (plan.sparse_ratio, plan.small_blocks) == best
+    assert _scaled_err(voltrix.spmm(*st, M, E, feat).cpu().numpy(), want) <= 1e-4
+    for a, b in zip(st, triple_before):                   # the reference-format triple never changes
+        assert torch.equal(a, b)
+    # a triple without the CSR arrays has nothing to route: no-op
+    st2 = voltrix.csr_preprocess(torch.from_numpy(indptr), torch.from_numpy(indices), M, keep_csr=False)
+    voltrix.reschedule(*st2, 1.0, 32)
+    assert st2[1]._vx_plan.num_sparse_rows == 0
+    assert voltrix.tune_routing(*st2, M, E, feat) == (None, {})

@@ -252,6 +252,10 @@ def spmm_kernel(
         keys = {"ctype": _CTYPE[input.dtype], "feature_hash": feature_hash(hspa_packed), "N": embedding_dim, "plan": caps}
 
     keys["weighted"] = "true" if weighted else "false"
+    if plan is not None and model is None and not getattr(plan, "route_is_default", True):
+        # a non-default routing rule (voltrix.reschedule / tune_routing) keeps its own winner even under a shared hash_tag;
+        # the default rule and the rule-less plan (no CSR arrays) keep the keys they always had
+        keys["route"] = f"{plan.sparse_ratio:g}/{plan.small_blocks}"
     keys["ft"] = 128          # default feature tile; a candidate that names its own overrides it
     if input.dtype == torch.float32 and model is None:
         keys["fp32"] = fp32_mode()      # winners are per precision class

@@ -11,4 +11,7 @@ from .spmm import (
     spmm_gcn,
     EdgeWeights,
     edge_weights,
+    reschedule,
+    tune_routing,
+    ROUTING_CANDIDATES,
 )

@@ -74,6 +74,11 @@ class SpmmPlan:
     def has_duplicates(self) -> bool:
         return self.unique_nnz != self.num_edges
 
+    @property
+    def route_is_default(self) -> bool:
+        """The routing rule csr_preprocess applies by default, or none at all (no CSR arrays to route with)."""
+        return self.csr_indptr is None or (self.sparse_ratio, self.small_blocks) == (DEFAULT_SPARSE_RATIO, DEFAULT_SMALL_BLOCKS)
+
     def signature(self) -> str:
         return f"M{self.num_nodes}_E{self.num_edges}_B{self.total_blocks}_I{self.num_items}_S{self.num_sparse_rows}"
 
@@ -98,6 +103,46 @@ class SpmmPlan:
 
 def _sm_count(device) -> int:
     return torch.cuda.get_device_properties(device).multi_processor_count
+
+
+def _build_schedule(plan: "SpmmPlan", pointer1: torch.Tensor, sparse_ratio: float, small_blocks: int) -> None:
+    """Phase 3 of ``csr_preprocess``: the nnz-balanced schedule (work items, fix-ups, CUDA-core row list) for a routing rule.
+    The tiles do not depend on the rule, so ``reschedule`` / ``tune_routing`` call this again on a finished triple."""
+    num_nodes, total_blocks, dev = plan.num_nodes, plan.total_blocks, pointer1.device
+    num_row_windows = math.ceil(num_nodes / BLK_H)
+    indptr = plan.csr_indptr
+    plan.sparse_ratio = float(sparse_ratio) if indptr is not None else 0.0
+    # phase 3: nnz-balanced schedule.  A window is split along K when it alone would exceed ~1/3 of an SM's share of
+    # the TC blocks (load balance: units are claimed dynamically in LPT order, so an item that size, started first, never
+    # forms the tail), and in any case beyond MAX_CHAIN_BLOCKS (accuracy: the tensor core adds each K-step
+    # into its fp32 accumulator with truncation, a bias that grows linearly with the length of one accumulation chain --
+    # 1.3e-3 relative on a 50 000-step chain of the R-MAT hub rows, measured against an fp64-accumulating oracle (1.3e-5
+    # with 1024-step chains); chunks of <= 2048 K-steps keep it below ~6e-5, and the chunks are summed in fp32
+    # round-to-nearest by the fix-up pass.  4096 blocks is above the largest window of the Reddit-shaped graph, whose
+    # shards therefore need no fix-up launch).
+    cap = max(64, min(MAX_CHAIN_BLOCKS, (total_blocks // (_sm_count(dev) * 3)) & ~1))
+    plan.cap = cap
+    max_items, sched_ws_bytes = schedule_sizes(num_nodes, total_blocks, cap)
+    sched_ws = alloc_workspace(sched_ws_bytes, dev)
+    fixups = torch.empty((max(num_row_windows, 1), 4), dtype=torch.int32, device=dev)
+    sparse_rows = torch.empty(max(num_nodes, 1), dtype=torch.int32, device=dev)
+    counts = torch.zeros(4, dtype=torch.int32, device=dev)
+    plan.small_blocks = int(small_blocks) if indptr is not None else 0
+    routing = plan.sparse_ratio > 0 or plan.small_blocks > 0
+    schedule_build_kernel(pointer1, plan.csr_indptr if routing else None, num_nodes, total_blocks, cap,
+                          plan.sparse_ratio, fixups, sparse_rows, counts, sched_ws, small_blocks=plan.small_blocks)
+    plan.num_items, plan.num_slots, plan.num_fixups, plan.num_sparse_rows = (int(v) for v in counts.tolist())
+    items = torch.empty((max(plan.num_items, 1), 4), dtype=torch.int32, device=dev)
+    schedule_sort_kernel(plan.num_items, num_nodes, total_blocks, cap, items, sched_ws)
+    plan.items = items
+    plan.fixups = fixups[: max(plan.num_fixups, 1)].clone()
+    plan.sparse_rows = sparse_rows[: max(plan.num_sparse_rows, 1)].clone()
+    plan.sparse_mean_degree = -1.0
+    if plan.num_sparse_rows > 0:
+        rows = plan.sparse_rows[: plan.num_sparse_rows].long()
+        plan.sparse_mean_degree = float((indptr[rows + 1] - indptr[rows]).sum().item()) / plan.num_sparse_rows
+    torch.cuda.current_stream().synchronize()
+    del sched_ws
 
 
 def csr_preprocess(
@@ -162,38 +207,8 @@ def csr_preprocess(
         # an edgeless matrix still needs a non-null indices pointer for the launch ABI
         plan.csr_indptr = indptr
         plan.csr_indices = indices if num_edges > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
-    plan.sparse_ratio = float(sparse_ratio) if use_csr else 0.0
-
-    # phase 3: nnz-balanced schedule.  A window is split along K when it alone would exceed ~1/3 of an SM's share of
-    # the TC blocks (load balance: units are claimed dynamically in LPT order, so an item that size, started first, never
-    # forms the tail), and in any case beyond MAX_CHAIN_BLOCKS (accuracy: the tensor core adds each K-step
-    # into its fp32 accumulator with truncation, a bias that grows linearly with the length of one accumulation chain --
-    # 1.3e-3 relative on a 50 000-step chain of the R-MAT hub rows, measured against an fp64-accumulating oracle (1.3e-5
-    # with 1024-step chains); chunks of <= 2048 K-steps keep it below ~6e-5, and the chunks are summed in fp32
-    # round-to-nearest by the fix-up pass.  4096 blocks is above the largest window of the Reddit-shaped graph, whose
-    # shards therefore need no fix-up launch).
-    cap = max(64, min(MAX_CHAIN_BLOCKS, (total_blocks // (_sm_count(dev) * 3)) & ~1))
-    plan.cap = cap
-    max_items, sched_ws_bytes = schedule_sizes(num_nodes, total_blocks, cap)
-    sched_ws = alloc_workspace(sched_ws_bytes, dev)
-    fixups = torch.empty((max(num_row_windows, 1), 4), dtype=torch.int32, device=dev)
-    sparse_rows = torch.empty(max(num_nodes, 1), dtype=torch.int32, device=dev)
-    counts = torch.zeros(4, dtype=torch.int32, device=dev)
-    plan.small_blocks = int(DEFAULT_SMALL_BLOCKS if small_blocks is None else small_blocks) if use_csr else 0
-    routing = plan.sparse_ratio > 0 or plan.small_blocks > 0
-    schedule_build_kernel(pointer1, plan.csr_indptr if routing else None, num_nodes, total_blocks, cap,
-                          plan.sparse_ratio, fixups, sparse_rows, counts, sched_ws, small_blocks=plan.small_blocks)
-    plan.num_items, plan.num_slots, plan.num_fixups, plan.num_sparse_rows = (int(v) for v in counts.tolist())
-    items = torch.empty((max(plan.num_items, 1), 4), dtype=torch.int32, device=dev)
-    schedule_sort_kernel(plan.num_items, num_nodes, total_blocks, cap, items, sched_ws)
-    plan.items = items
-    plan.fixups = fixups[: max(plan.num_fixups, 1)].clone()
-    plan.sparse_rows = sparse_rows[: max(plan.num_sparse_rows, 1)].clone()
-    if plan.num_sparse_rows > 0:
-        rows = plan.sparse_rows[: plan.num_sparse_rows].long()
-        plan.sparse_mean_degree = float((indptr[rows + 1] - indptr[rows]).sum().item()) / plan.num_sparse_rows
-    torch.cuda.current_stream().synchronize()
-    del sched_ws
+    _build_schedule(plan, pointer1, sparse_ratio if use_csr else 0.0,
+                    int(DEFAULT_SMALL_BLOCKS if small_blocks is None else small_blocks) if use_csr else 0)
 
     hspa_packed._vx_plan = plan
     return (
@@ -201,6 +216,67 @@ def csr_preprocess(
         hspa_packed,
         hind,
     )
+
+
+# Candidate routing rules of ``tune_routing``: (sparse_ratio, small_blocks).  (0, 0) = everything on the tensor cores.
+ROUTING_CANDIDATES = ((DEFAULT_SPARSE_RATIO, DEFAULT_SMALL_BLOCKS), (0.25, DEFAULT_SMALL_BLOCKS), (1.0, DEFAULT_SMALL_BLOCKS),
+                      (DEFAULT_SPARSE_RATIO, 0), (DEFAULT_SPARSE_RATIO, 32), (1.0, 32), (0.0, 0))
+
+
+def reschedule(blk_offsets: torch.Tensor, hspa_packed: torch.Tensor, hind: torch.Tensor,
+               sparse_ratio: Optional[float] = None, small_blocks: Optional[int] = None) -> None:
+    """Rebuild the work list of a preprocessed matrix under another routing rule (which windows run on the CUDA-core rows
+    instead of the tensor cores; ``schedule.cuh``), in place.  The reference-format triple is untouched -- only the plan
+    hung off ``hspa_packed`` changes -- so this costs the schedule kernels alone (a few ms), not a preprocessing pass.
+    Without the CSR arrays (``keep_csr=False`` or duplicated entries) there is nothing to route and the call is a no-op."""
+    plan = getattr(hspa_packed, "_vx_plan", None)
+    if plan is None:
+        raise ValueError("reschedule: this triple carries no plan (it did not come from csr_preprocess / load_preprocessed)")
+    if plan.csr_indptr is None:
+        return
+    _build_schedule(plan, blk_offsets, plan.sparse_ratio if sparse_ratio is None else float(sparse_ratio),
+                    plan.small_blocks if small_blocks is None else int(small_blocks))
+    plan._scratch.clear()                         # the number of K-split slots changed
+    for attr in ("_vx_fast",):                    # prepared launches bake the old work list in
+        if hasattr(hspa_packed, attr):
+            getattr(hspa_packed, attr).clear()
+
+
+def tune_routing(blk_offsets: torch.Tensor, hspa_packed: torch.Tensor, hind: torch.Tensor, num_nodes: int, num_edges: int,
+                 feat: torch.Tensor, candidates=ROUTING_CANDIDATES, iters: int = 5):
+    """Pick the routing rule by measurement (the density threshold is part of the tune space).
+
+    For every ``(sparse_ratio, small_blocks)`` candidate the plan is rescheduled, ``spmm`` runs on ``feat`` (its own kernel
+    autotune included: the tune key carries the plan's shape statistics, so each rule keeps its own winner) and is timed
+    with CUDA events behind a 256 MB L2 flush; the fastest rule is left installed.  Returns ``(best_rule, {rule: ms})``.
+    Deterministic given the timings' order; results are unchanged (every rule computes the same sums, on different units)."""
+    plan = getattr(hspa_packed, "_vx_plan", None)
+    if plan is None or plan.csr_indptr is None:
+        return None, {}
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=feat.device)
+    out = torch.empty((num_nodes, feat.shape[1]), dtype=torch.float32, device=feat.device)
+    seen, timings = set(), {}
+    for rule in candidates:
+        rule = (float(rule[0]), int(rule[1]))
+        reschedule(blk_offsets, hspa_packed, hind, *rule)
+        shape = (plan.num_items, plan.num_sparse_rows, plan.num_fixups)
+        if shape in seen:                         # this rule routes exactly like an earlier one
+            continue
+        seen.add(shape)
+        spmm(blk_offsets, hspa_packed, hind, num_nodes, num_edges, feat, out=out)      # tune / load
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            spmm(blk_offsets, hspa_packed, hind, num_nodes, num_edges, feat, out=out)
+            t1.record()
+            t1.synchronize()
+            ts.append(t0.elapsed_time(t1))
+        timings[rule] = sorted(ts)[len(ts) // 2]
+    best = min(timings, key=timings.get)
+    reschedule(blk_offsets, hspa_packed, hind, *best)
+    return best, timings
 
 
 def spmm(
