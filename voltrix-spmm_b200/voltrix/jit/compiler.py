@@ -20,7 +20,7 @@ import subprocess
 import uuid
 from typing import Tuple, cast
 
-from ..project import (CACHE_DIR_FLAG, DEBUG_FLAG, JIT_PRINT_NVCC_COMMAND_FLAG, NVCC_COMPILER_FLAG,
+from ..project import (CACHE_DIR_FLAG, DEBUG_FLAG, EXTRA_NVCC_FLAGS_FLAG, JIT_PRINT_NVCC_COMMAND_FLAG, NVCC_COMPILER_FLAG,
                        PROJECT_NAME_ABBR_LOWER, PTXAS_VERBOSE_FLAG)
 from .runtime import Runtime, RuntimeCache
 from .template import typename_map
@@ -136,7 +136,7 @@ def nvcc_flags() -> list:
     ]
     if PTXAS_VERBOSE_FLAG in os.environ:
         flags.append("--ptxas-options=-v")
-    flags += os.environ.get("VOLTRIX_EXTRA_NVCC_FLAGS", "").split()   # experiments; part of the cache key
+    flags += os.environ.get(EXTRA_NVCC_FLAGS_FLAG, "").split()   # experiments; part of the cache key
     cxx_flags = ["-fPIC", "-O3", "-Wno-deprecated-declarations", "-Wno-abi", "-fno-gnu-unique"]
     return [*flags, f'--compiler-options={",".join(cxx_flags)}']
 

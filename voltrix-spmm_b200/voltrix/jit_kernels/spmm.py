@@ -16,6 +16,7 @@ import warnings
 import torch
 
 from ..jit.compiler import hash_to_hex
+from ..project import FP32_EXACT_FLAG, FP32_MODE_FLAG
 from ._common import check, current_stream
 from .tuner import jit_tuner
 
@@ -141,7 +142,7 @@ def _ticket(owner, device, stream_id: int) -> torch.Tensor:
 
 def fp32_mode() -> str:
     import os
-    return os.environ.get("VOLTRIX_FP32_MODE", "exact" if os.environ.get("VOLTRIX_FP32_EXACT", "0") == "1" else "tf32")
+    return os.environ.get(FP32_MODE_FLAG, "exact" if os.environ.get(FP32_EXACT_FLAG, "0") == "1" else "tf32")
 
 
 def fp32_space():
