@@ -1,4 +1,4 @@
-"""voltrix.tune_routing on C3 shapes: default routing rule (sparse_ratio 0.5, small_blocks 8) against the measured best of
+"""voltrix.tune_routing on C3 shapes: the routing rule csr_preprocess installs (sparse_ratio 0.5; small_blocks 8 from 4 M TC blocks up, else 0) against the measured best of
 voltrix.ROUTING_CANDIDATES, per graph / width / dtype.
 
     python scripts/routing_probe.py [--datasets ppi protein ...] [--feature_dims 64 128 256] [--out gpurun_out/routing.csv]"""
@@ -32,13 +32,14 @@ with open(args.out, "w", newline="") as fh:
             for dtype in (torch.float16, torch.float32):
                 feat = torch.rand(M, N, device=dev).to(dtype)
                 want = voltrix.spmm(*st, M, nnz, feat)
+                installed = (st[1]._vx_plan.sparse_ratio, st[1]._vx_plan.small_blocks)
                 best, timings = voltrix.tune_routing(*st, M, nnz, feat)
                 got = voltrix.spmm(*st, M, nnz, feat)
                 err = float((got - want).abs().max() / want.abs().max().clamp_min(1e-9))
-                default = timings[tuple(map(float, voltrix.ROUTING_CANDIDATES[0][:1])) + (int(voltrix.ROUTING_CANDIDATES[0][1]),)]
+                default = timings[installed]
                 row = [name, N, str(dtype)[6:], f"{default:.4f}", f"{best[0]:g}/{best[1]}", f"{timings[best]:.4f}",
                        f"{default / timings[best]:.3f}", " ".join(f"{k[0]:g}/{k[1]}:{v:.4f}" for k, v in timings.items())]
                 assert err < 2e-3, (name, N, dtype, err)
                 w.writerow(row); fh.flush()
                 print(" ".join(str(x) for x in row), flush=True)
-                voltrix.reschedule(*st, *voltrix.ROUTING_CANDIDATES[0])
+                voltrix.reschedule(*st, *installed)

@@ -259,7 +259,8 @@ def test_short_rows_at_scale_take_several_rows_per_warp(dtype, N):
     assert np.isfinite(got).all() and _scaled_err(got, want) <= TOL[dtype]
     if dtype == torch.float32:
         assert np.array_equal(got[deg <= 8], want[deg <= 8])
-    assert st[1]._vx_plan.num_sparse_rows >= (1 << 17)                                # the row-list launch is RPW too
+    voltrix.reschedule(*st, 4.0, 0)                  # route (nearly) every window to the CUDA-core rows: the row-list launch
+    assert st[1]._vx_plan.num_sparse_rows >= (1 << 17)                                # ... is RPW too
     auto = voltrix.spmm(*st, M, indices.size, feat)
     assert _scaled_err(auto.cpu().numpy(), want) <= max(TOL[dtype], 2e-3 if dtype == torch.float32 else 0)
     vals = rng.uniform(0.5, 1.5, indices.size).astype(np.float32)

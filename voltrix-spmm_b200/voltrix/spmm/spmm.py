@@ -41,7 +41,11 @@ BLK_W = 8
 # SPARSE_RATIO x the rows the tensor-core path would gather for it (16 per K-step).
 DEFAULT_SPARSE_RATIO = 0.5
 # Windows of at most this many TC blocks go to the CUDA-core rows whenever they contain any padding (see schedule.cuh).
+# The rule pays on matrices with millions of tiny windows (R-MAT: -10 %, profiles/r2k_small_blocks_sweep.txt) and costs a
+# second kernel launch -- 4-8 us, up to 33 % of the whole SpMM -- on small ones (protein, DD, com-amazon:
+# profiles/r2ae_routing_probe.csv, r2ag_routing_probe_more.csv), so by default it applies from SMALL_BLOCKS_MIN_TCB blocks up.
 DEFAULT_SMALL_BLOCKS = 8
+SMALL_BLOCKS_MIN_TCB = 4_000_000
 # Longest run of TC blocks one work item accumulates in the tensor core before its partial tile is handed to the fix-up pass.
 MAX_CHAIN_BLOCKS = 4096
 
@@ -77,7 +81,7 @@ class SpmmPlan:
     @property
     def route_is_default(self) -> bool:
         """The routing rule csr_preprocess applies by default, or none at all (no CSR arrays to route with)."""
-        return self.csr_indptr is None or (self.sparse_ratio, self.small_blocks) == (DEFAULT_SPARSE_RATIO, DEFAULT_SMALL_BLOCKS)
+        return self.csr_indptr is None or (self.sparse_ratio, self.small_blocks) == default_routing(self.total_blocks)
 
     def signature(self) -> str:
         return f"M{self.num_nodes}_E{self.num_edges}_B{self.total_blocks}_I{self.num_items}_S{self.num_sparse_rows}"
@@ -99,6 +103,11 @@ class SpmmPlan:
                 self.scratch(embedding_dim, stream_id), self.csr_indptr, self.csr_indices,
                 self.sparse_rows if self.num_sparse_rows else None, self.num_sparse_rows,
                 float(self.sparse_mean_degree))
+
+
+def default_routing(total_blocks: int):
+    """``(sparse_ratio, small_blocks)`` csr_preprocess applies when the caller names neither."""
+    return DEFAULT_SPARSE_RATIO, (DEFAULT_SMALL_BLOCKS if total_blocks >= SMALL_BLOCKS_MIN_TCB else 0)
 
 
 def _sm_count(device) -> int:
@@ -208,7 +217,7 @@ def csr_preprocess(
         plan.csr_indptr = indptr
         plan.csr_indices = indices if num_edges > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
     _build_schedule(plan, pointer1, sparse_ratio if use_csr else 0.0,
-                    int(DEFAULT_SMALL_BLOCKS if small_blocks is None else small_blocks) if use_csr else 0)
+                    int(default_routing(total_blocks)[1] if small_blocks is None else small_blocks) if use_csr else 0)
 
     hspa_packed._vx_plan = plan
     return (
@@ -218,9 +227,10 @@ def csr_preprocess(
     )
 
 
-# Candidate routing rules of ``tune_routing``: (sparse_ratio, small_blocks).  (0, 0) = everything on the tensor cores.
-ROUTING_CANDIDATES = ((DEFAULT_SPARSE_RATIO, DEFAULT_SMALL_BLOCKS), (0.25, DEFAULT_SMALL_BLOCKS), (1.0, DEFAULT_SMALL_BLOCKS),
-                      (DEFAULT_SPARSE_RATIO, 0), (DEFAULT_SPARSE_RATIO, 32), (1.0, 32), (0.0, 0))
+# Candidate routing rules of ``tune_routing``: (sparse_ratio, small_blocks); the installed rule is always timed first.
+# (0, 0) = everything on the tensor cores.
+ROUTING_CANDIDATES = ((DEFAULT_SPARSE_RATIO, 0), (DEFAULT_SPARSE_RATIO, DEFAULT_SMALL_BLOCKS), (0.25, 0), (1.0, 0),
+                      (DEFAULT_SPARSE_RATIO, 32), (1.0, 32), (0.0, 0))
 
 
 def reschedule(blk_offsets: torch.Tensor, hspa_packed: torch.Tensor, hind: torch.Tensor,
@@ -256,7 +266,7 @@ def tune_routing(blk_offsets: torch.Tensor, hspa_packed: torch.Tensor, hind: tor
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=feat.device)
     out = torch.empty((num_nodes, feat.shape[1]), dtype=torch.float32, device=feat.device)
     seen, timings = set(), {}
-    for rule in candidates:
+    for rule in ((plan.sparse_ratio, plan.small_blocks),) + tuple(candidates):
         rule = (float(rule[0]), int(rule[1]))
         reschedule(blk_offsets, hspa_packed, hind, *rule)
         shape = (plan.num_items, plan.num_sparse_rows, plan.num_fixups)
