@@ -170,25 +170,29 @@ inline int voltrix_spmm_forward_cuda(const int32_t *blks_offsets, const uint32_t
       int32_t *flag = plan.ticket + 1;       // ticket[1..3]: flag, bits of max |x|, tail-group count
       __half *as_half = static_cast<__half *>(plan.split_ws);
       __nv_bfloat16 *terms = static_cast<__nv_bfloat16 *>(plan.split_ws);
-      int rc = launch_cvt_f16(input, as_half, b_rows, embedding_dim, flag, stream);
+      // one memset for the whole call: the unit ticket (only one of the two gated tensor-core launches ever claims
+      // from it) and the three state words of the conversion pass
+      VX_CUDA_TRY(cudaMemsetAsync(plan.ticket, 0, 4 * sizeof(int32_t), stream));
+      int rc = launch_cvt_f16(input, as_half, b_rows, embedding_dim, flag, stream, /*state_zeroed=*/true);
       if (rc != VX_OK) return rc;
       Epilogue carried = plan.epilogue;      // the fp16 carrier is 2^s times the operand: scale the accumulator back
       carried.pow2_max_bits = flag + 1;
       if (embedding_dim <= 64)   // the 64-wide feature tile, as for 16-bit operands of that width
         rc = launch_spmm_tc<__half, 20, 10, 1, false, 64>(plan.items, plan.num_items, plan.fixups, plan.num_fixups,
                                                           blks_offsets, hspa_packed, hind, num_nodes, b_rows, embedding_dim,
-                                                          as_half, output, plan.scratch, stream, carried, plan.ticket, flag, 0);
+                                                          as_half, output, plan.scratch, stream, carried, plan.ticket, flag, 0,
+                                                          /*reset_ticket=*/false);
       else
         rc = launch_spmm_tc<__half, 14, 7, 1>(plan.items, plan.num_items, plan.fixups, plan.num_fixups, blks_offsets,
                                               hspa_packed, hind, num_nodes, b_rows, embedding_dim, as_half, output,
-                                              plan.scratch, stream, carried, plan.ticket, flag, 0);
+                                              plan.scratch, stream, carried, plan.ticket, flag, 0, /*reset_ticket=*/false);
       if (rc != VX_OK) return rc;
       rc = launch_split_bf16x2(input, terms, b_rows, embedding_dim, stream, flag, 1);
       if (rc != VX_OK) return rc;
       rc = launch_spmm_tc<__nv_bfloat16, STAGES, NPW, 2>(plan.items, plan.num_items, plan.fixups, plan.num_fixups,
                                                          blks_offsets, hspa_packed, hind, num_nodes, b_rows, embedding_dim,
                                                          terms, output, plan.scratch, stream, plan.epilogue, plan.ticket,
-                                                         flag, 1);
+                                                         flag, 1, /*reset_ticket=*/false);
       if (rc != VX_OK) return rc;
       if (plan.num_sparse_rows > 0) {   // sparse windows: exact fp32 rows from the original operand
         if (!plan.csr_indptr || !plan.csr_indices || !plan.sparse_rows) return VX_ERR_INVALID_ARG;

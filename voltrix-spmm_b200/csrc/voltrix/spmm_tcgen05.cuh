@@ -609,7 +609,7 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
                           int32_t num_nodes, int64_t b_rows,
                           int32_t N, const T *B, float *C, float *scratch, cudaStream_t stream,
                           const Epilogue &epi = Epilogue(), int32_t *ticket = nullptr, const int32_t *gate = nullptr,
-                          int32_t gate_want = 0) {
+                          int32_t gate_want = 0, bool reset_ticket = true) {
   if (num_items <= 0) return VX_OK;
   if (N % 8 != 0 || (reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(hind) & 15) ||
       (reinterpret_cast<uintptr_t>(hspa_packed) & 15))
@@ -630,7 +630,8 @@ inline int launch_spmm_tc(const WorkItem *items, int32_t num_items, const FixupI
   const int grid = int(total_units < resident ? total_units : resident);
   // `ticket` (4 bytes of device memory owned by the caller, one per stream in flight): dynamic unit claiming.
   // Zeroed here, on the stream, so a launch never depends on how the previous one ended; nullptr = static striding.
-  if (ticket != nullptr) VX_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int32_t), stream));
+  // reset_ticket = false: the caller has zeroed it already on this stream (the gated pipelines of model 4 share one memset).
+  if (ticket != nullptr && reset_ticket) VX_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int32_t), stream));
   kern<<<grid, G::kThreads, smem, stream>>>(tmap, items, num_items, n_feat_tiles, blk_offsets,
                                                  reinterpret_cast<const uint4 *>(hspa_packed),
                                                  reinterpret_cast<const int4 *>(hind), num_nodes, N, C, scratch, N, epi,
@@ -750,10 +751,12 @@ __global__ void vx_spmm_f16_gate_kernel(int32_t *__restrict__ state, int32_t lim
 }
 
 // state: 3 ints of device memory (flag, max bits, tail count), initialised here
-inline int launch_cvt_f16(const float *in, __half *out, int64_t rows, int32_t N, int32_t *state, cudaStream_t stream) {
+// state_zeroed: the caller has already zeroed the three words on this stream
+inline int launch_cvt_f16(const float *in, __half *out, int64_t rows, int32_t N, int32_t *state, cudaStream_t stream,
+                          bool state_zeroed = false) {
   if (N % 4 != 0 || (reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || state == nullptr)
     return VX_ERR_UNSUPPORTED;
-  VX_CUDA_TRY(cudaMemsetAsync(state, 0, 3 * sizeof(int32_t), stream));      // flag = 0, max |x| = 0, tail groups = 0
+  if (!state_zeroed) VX_CUDA_TRY(cudaMemsetAsync(state, 0, 3 * sizeof(int32_t), stream));   // flag, max |x|, tail groups
   const int64_t quads = rows * (N >> 2);
   if (quads <= 0) return VX_OK;
   const int64_t groups = (quads + 31) / 32;                                 // 128-value groups = warps of the convert pass
