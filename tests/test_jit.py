@@ -130,3 +130,34 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "voltrix_oracle" not in text, f
+
+
+def test_environment_flag_spellings_are_the_references():
+    # reference voltrix/project/const.py:2-14: the values, not just the names, are the contract (shells export them)
+    assert (voltrix.PROJECT_NAME_FULL, voltrix.PROJECT_NAME_ABBR) == ("Voltrix-SpMM", "Voltrix")
+    assert (voltrix.PROJECT_NAME_FULL_LOWER, voltrix.PROJECT_NAME_ABBR_LOWER) == ("voltrix-spmm", "voltrix")
+    assert voltrix.DEBUG_FLAG == "VOLTRIX_JIT_DEBUG" and voltrix.NVCC_COMPILER_FLAG == "VOLTRIX_NVCC_COMPILER"
+    assert voltrix.CACHE_DIR_FLAG == "VOLTRIX_CACHE_DIR" and voltrix.PTXAS_VERBOSE_FLAG == "VOLTRIX_PTXAS_VERBOSE"
+    assert voltrix.JIT_PRINT_NVCC_COMMAND_FLAG == "VOLTRIX_JIT_PRINT_NVCC_COMMAND"
+    assert voltrix.PRINT_AUTOTUNE_FLAG == "VOLTRIX_PRINT_AUTO_TUNE"
+    assert voltrix.FP32_MODE_FLAG == "VOLTRIX_FP32_MODE" and voltrix.EXTRA_NVCC_FLAGS_FLAG == "VOLTRIX_EXTRA_NVCC_FLAGS"
+
+
+def test_default_routing_rule_depends_on_size_only():
+    """csr_preprocess's default (sparse_ratio, small_blocks): the small-window rule is on from SMALL_BLOCKS_MIN_TCB TC blocks
+    up (it costs a second launch on small matrices); a plan without CSR arrays has no rule to deviate from."""
+    from voltrix.spmm.spmm import SMALL_BLOCKS_MIN_TCB, SpmmPlan, default_routing
+    assert default_routing(0) == (0.5, 0) and default_routing(SMALL_BLOCKS_MIN_TCB - 1) == (0.5, 0)
+    assert default_routing(SMALL_BLOCKS_MIN_TCB) == (0.5, 8) and default_routing(10 ** 9) == (0.5, 8)
+    assert voltrix.ROUTING_CANDIDATES[0] == (0.5, 0) and (0.5, 8) in voltrix.ROUTING_CANDIDATES
+    plan = SpmmPlan()
+    plan.total_blocks, plan.sparse_ratio, plan.small_blocks = 1000, 0.0, 0
+    assert plan.route_is_default                        # no CSR arrays
+    plan.csr_indptr = torch.zeros(2, dtype=torch.int32)
+    assert not plan.route_is_default
+    plan.sparse_ratio = 0.5
+    assert plan.route_is_default
+    plan.total_blocks = SMALL_BLOCKS_MIN_TCB
+    assert not plan.route_is_default
+    plan.small_blocks = 8
+    assert plan.route_is_default
